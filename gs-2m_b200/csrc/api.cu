@@ -1,0 +1,294 @@
+// C-ABI entry points (include/gs2m_rasterizer.h) and host orchestration of the stages.
+//
+// Behavioural reference: CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (cuda_rasterizer/rasterizer_impl.cu:185-330, 334-438, 132-143) and the torch glue's argument checks
+// (rasterize_points.cu:52-54,78,161).  Differences that matter to callers: kernels run on the caller's stream
+// (the reference uses the legacy default stream), every CUDA call is checked, and outputs need no pre-zeroing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace gs2m {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+bool check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return false;
+}
+
+size_t GeomState::carve(char* base, int P, GeomState* out) {
+    GeomState g;
+    char* p = base;
+    const size_t n = (size_t)P;
+    carve_array(p, g.depths, n);
+    carve_array(p, g.xy_conic_ab, n);
+    carve_array(p, g.conic_c_opac, n);
+    carve_array(p, g.rgb, n);
+    carve_array(p, g.cov3D, n * 6);
+    carve_array(p, g.clamped, n * 4);
+    carve_array(p, g.tiles_touched, n);
+    carve_array(p, g.point_offsets, n);
+    carve_array(p, g.scan_temp, scan_temp_bytes(P));
+    carve_array(p, g.grad_acc, n * GS2M_ACC_STRIDE);
+    if (out) *out = g;
+    return (size_t)(p - base) + 128;
+}
+
+size_t BinState::carve(char* base, int R, BinState* out) {
+    BinState b;
+    char* p = base;
+    const size_t n = (size_t)(R > 0 ? R : 0);
+    carve_array(p, b.keys_unsorted, n);
+    carve_array(p, b.keys_sorted, n);
+    carve_array(p, b.vals_unsorted, n);
+    carve_array(p, b.point_list, n);
+    carve_array(p, b.sort_temp, sort_temp_bytes(R));
+    if (out) *out = b;
+    return (size_t)(p - base) + 128;
+}
+
+size_t ImageState::carve(char* base, int W, int H, ImageState* out) {
+    ImageState im;
+    char* p = base;
+    const size_t n = (size_t)W * H;
+    const size_t tiles = (size_t)((W + GS2M_TILE_X - 1) / GS2M_TILE_X) * ((H + GS2M_TILE_Y - 1) / GS2M_TILE_Y);
+    carve_array(p, im.final_T, n);
+    carve_array(p, im.n_contrib, n);
+    carve_array(p, im.ranges, tiles);
+    if (out) *out = im;
+    return (size_t)(p - base) + 128;
+}
+
+// bit_length(n): number of key bits the tile id needs (getHigherMsb, rasterizer_impl.cu:31-44)
+static int tile_bits(uint32_t n_tiles) {
+    int b = 0;
+    while (n_tiles >> b) ++b;
+    return b;
+}
+
+// The sorted lists end in the "unsorted" buffers when the digit-pass count is even (no final copy is made).
+static void resolve_sorted(const BinState& b, int n_tiles, const uint64_t*& keys, const uint32_t*& vals) {
+    const int passes = (32 + tile_bits((uint32_t)n_tiles) + 7) / 8;
+    if (passes & 1) { keys = b.keys_sorted; vals = b.point_list; }
+    else            { keys = b.keys_unsorted; vals = b.vals_unsorted; }
+}
+
+static int validate_common(int P, int D, int M, int W, int H, int F, const void* means3D, const void* shs,
+                           const void* colors_precomp, const void* scales, const void* rotations, const void* cov3D,
+                           const void* features, const void* vm, const void* pm, const void* cam) {
+    if (P < 0 || W <= 0 || H <= 0) { set_error("invalid sizes P=%d W=%d H=%d", P, W, H); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (F < 0 || F > GS2M_NUM_FEATURES) { set_error("feature_count %d outside 0..10", F); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (P == 0) return GS2M_OK;
+    if (!means3D || !vm || !pm) { set_error("means3D / viewmatrix / projmatrix must not be NULL"); return GS2M_ERR_INVALID_ARGUMENT; }
+    if ((shs == nullptr) == (colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (shs && (M <= 0 || D < 0 || D > 3 || (D + 1) * (D + 1) > M)) { set_error("SH degree %d does not fit M=%d coefficients", D, M); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (shs && !cam) { set_error("cam_pos must not be NULL when shs are used"); return GS2M_ERR_INVALID_ARGUMENT; }
+    const bool have_sr = scales != nullptr && rotations != nullptr;
+    if (have_sr == (cov3D != nullptr) || ((scales != nullptr) != (rotations != nullptr))) {
+        set_error("provide exactly one of scales+rotations / cov3D_precomp"); return GS2M_ERR_INVALID_ARGUMENT;
+    }
+    if (F > 0 && !features) { set_error("features must not be NULL when feature_count > 0"); return GS2M_ERR_INVALID_ARGUMENT; }
+    return GS2M_OK;
+}
+
+}  // namespace gs2m
+
+using namespace gs2m;
+
+extern "C" {
+
+int gs2m_abi_version(void) { return GS2M_ABI_VERSION; }
+const char* gs2m_last_error(void) { return g_error; }
+
+size_t gs2m_geometry_bytes(int P) { return GeomState::carve(nullptr, P, nullptr); }
+size_t gs2m_image_bytes(int width, int height) { return ImageState::carve(nullptr, width, height, nullptr); }
+size_t gs2m_binning_bytes(int R) { return BinState::carve(nullptr, R, nullptr); }
+size_t gs2m_sort_temp_bytes(int n) { return sort_temp_bytes(n); }
+size_t gs2m_scan_temp_bytes(int n) { return scan_temp_bytes(n); }
+
+int gs2m_sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit,
+                        char* temp, void* stream) {
+    return sort_pairs_u64(keys_in, keys_out, vals_in, vals_out, n, end_bit, temp, (cudaStream_t)stream);
+}
+
+int gs2m_inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, void* stream) {
+    return inclusive_sum_u32(in, out, n, temp, (cudaStream_t)stream);
+}
+
+int gs2m_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                      void* stream) {
+    (void)projmatrix;  // the reference's frustum test only uses the view matrix (auxiliary.h:148-152)
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("mark_visible: bad arguments"); return GS2M_ERR_INVALID_ARGUMENT; }
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int gs2m_rasterize_forward(const gs2m_forward_args* a) {
+    if (!a) { set_error("null args"); return GS2M_ERR_INVALID_ARGUMENT; }
+    int rc = validate_common(a->P, a->D, a->M, a->width, a->height, a->feature_count, a->means3D, a->shs, a->colors_precomp,
+                             a->scales, a->rotations, a->cov3D_precomp, a->features, a->viewmatrix, a->projmatrix, a->cam_pos);
+    if (rc != GS2M_OK) return rc;
+    if (!a->out_color || !a->out_buffer || !a->background || (a->P > 0 && (!a->out_radii || !a->out_observe || !a->opacities))) {
+        set_error("forward: missing output / background / opacity pointer"); return GS2M_ERR_INVALID_ARGUMENT;
+    }
+    if (!a->geometry_buffer || !a->binning_buffer || !a->image_buffer) { set_error("forward: missing resize callbacks"); return GS2M_ERR_INVALID_ARGUMENT; }
+    cudaStream_t s = (cudaStream_t)a->stream;
+
+    FwdParams p;
+    p.P = a->P; p.D = a->D; p.M = a->M; p.W = a->width; p.H = a->height; p.F = a->feature_count;
+    p.tiles_x = (a->width + GS2M_TILE_X - 1) / GS2M_TILE_X;
+    p.tiles_y = (a->height + GS2M_TILE_Y - 1) / GS2M_TILE_Y;
+    p.tan_fovx = a->tan_fovx; p.tan_fovy = a->tan_fovy;
+    p.focal_y = a->height / (2.0f * a->tan_fovy);   // rasterizer_impl.cu:212-213
+    p.focal_x = a->width / (2.0f * a->tan_fovx);
+    p.scale_modifier = a->scale_modifier;
+    p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp; p.opacities = a->opacities;
+    p.scales = a->scales; p.rotations = a->rotations; p.cov3D_precomp = a->cov3D_precomp; p.features = a->features;
+    p.viewmatrix = a->viewmatrix; p.projmatrix = a->projmatrix; p.cam_pos = a->cam_pos; p.background = a->background;
+    const int n_tiles = p.tiles_x * p.tiles_y;
+
+    char* img_base = a->image_buffer(a->image_user, ImageState::carve(nullptr, p.W, p.H, nullptr));
+    if (!img_base) { set_error("image_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
+    ImageState im;
+    ImageState::carve(img_base, p.W, p.H, &im);
+
+    int R = 0;
+    GeomState g;
+    memset(&g, 0, sizeof(g));
+    const uint32_t* point_list = nullptr;
+    if (p.P > 0) {
+        char* geom_base = a->geometry_buffer(a->geometry_user, GeomState::carve(nullptr, p.P, nullptr));
+        if (!geom_base) { set_error("geometry_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
+        GeomState::carve(geom_base, p.P, &g);
+
+        rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, s);
+        if (rc != GS2M_OK) return rc;
+        rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s);
+        if (rc != GS2M_OK) return rc;
+        // the instance count sizes the binning arena: one device->host read, like rasterizer_impl.cu:269-270
+        uint32_t r_host = 0;
+        GS2M_CUDA(cudaMemcpyAsync(&r_host, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        GS2M_CUDA(cudaStreamSynchronize(s));
+        if (r_host >= (1u << 30)) { set_error("%u Gaussian/tile instances exceed the supported 2^30", r_host); return GS2M_ERR_TOO_LARGE; }
+        R = (int)r_host;
+    }
+
+    char* bin_base = a->binning_buffer(a->binning_user, BinState::carve(nullptr, R, nullptr));
+    if (!bin_base) { set_error("binning_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
+    BinState b;
+    BinState::carve(bin_base, R, &b);
+    const uint64_t* keys_sorted = b.keys_sorted;
+    point_list = b.point_list;
+    if (R > 0) {
+        rc = launch_duplicate_with_keys(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, b.keys_unsorted, b.vals_unsorted, s);
+        if (rc != GS2M_OK) return rc;
+        int in_input = 0;
+        rc = sort_pairs_u64_pingpong(b.keys_unsorted, b.keys_sorted, b.vals_unsorted, b.point_list, R,
+                                     32 + tile_bits((uint32_t)n_tiles), b.sort_temp, s, &in_input);
+        if (rc != GS2M_OK) return rc;
+        resolve_sorted(b, n_tiles, keys_sorted, point_list);
+        if ((keys_sorted == b.keys_unsorted) != (in_input != 0)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
+    }
+    rc = launch_identify_tile_ranges(R, keys_sorted, im.ranges, n_tiles, s);
+    if (rc != GS2M_OK) return rc;
+    rc = launch_blend_forward(p, g, point_list, im, a->out_color, a->out_observe, a->out_buffer, s);
+    if (rc != GS2M_OK) return rc;
+    return R;
+}
+
+int gs2m_rasterize_backward(const gs2m_backward_args* a) {
+    if (!a) { set_error("null args"); return GS2M_ERR_INVALID_ARGUMENT; }
+    int rc = validate_common(a->P, a->D, a->M, a->width, a->height, a->feature_count, a->means3D, a->shs, a->colors_precomp,
+                             a->scales, a->rotations, a->cov3D_precomp, a->features, a->viewmatrix, a->projmatrix, a->cam_pos);
+    if (rc != GS2M_OK) return rc;
+    if (a->P == 0) return GS2M_OK;
+    if (!a->radii || !a->geometry_buffer || !a->binning_buffer || !a->image_buffer || !a->grad_color ||
+        (a->feature_count > 0 && !a->grad_buffer) || !a->background) {
+        set_error("backward: missing saved state / upstream gradient pointer"); return GS2M_ERR_INVALID_ARGUMENT;
+    }
+    if (!a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dmeans3D || !a->dL_dcov3D || !a->dL_dscale ||
+        !a->dL_drot || !a->dL_dfeatures || (a->M > 0 && a->shs && !a->dL_dsh)) {
+        set_error("backward: missing gradient output pointer"); return GS2M_ERR_INVALID_ARGUMENT;
+    }
+    if (a->R < 0) { set_error("backward: negative R"); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (a->geometry_bytes < GeomState::carve(nullptr, a->P, nullptr) ||
+        a->binning_bytes < BinState::carve(nullptr, a->R, nullptr) ||
+        a->image_bytes < ImageState::carve(nullptr, a->width, a->height, nullptr)) {
+        set_error("backward: a saved arena is smaller than forward allocated it"); return GS2M_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = (cudaStream_t)a->stream;
+
+    BwdParams p;
+    p.P = a->P; p.D = a->D; p.M = a->M; p.W = a->width; p.H = a->height; p.F = a->feature_count; p.R = a->R;
+    p.tiles_x = (a->width + GS2M_TILE_X - 1) / GS2M_TILE_X;
+    p.tiles_y = (a->height + GS2M_TILE_Y - 1) / GS2M_TILE_Y;
+    p.tan_fovx = a->tan_fovx; p.tan_fovy = a->tan_fovy;
+    p.focal_y = a->height / (2.0f * a->tan_fovy);
+    p.focal_x = a->width / (2.0f * a->tan_fovx);
+    p.scale_modifier = a->scale_modifier;
+    p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp; p.scales = a->scales;
+    p.rotations = a->rotations; p.cov3D_precomp = a->cov3D_precomp; p.features = a->features;
+    p.viewmatrix = a->viewmatrix; p.projmatrix = a->projmatrix; p.cam_pos = a->cam_pos; p.background = a->background;
+    p.radii = a->radii; p.grad_color = a->grad_color; p.grad_buffer = a->grad_buffer;
+    p.dL_dmeans2D = a->dL_dmeans2D; p.dL_dconic = a->dL_dconic; p.dL_dopacity = a->dL_dopacity; p.dL_dcolor = a->dL_dcolor;
+    p.dL_dmeans3D = a->dL_dmeans3D; p.dL_dcov3D = a->dL_dcov3D; p.dL_dsh = a->dL_dsh; p.dL_dscale = a->dL_dscale;
+    p.dL_drot = a->dL_drot; p.dL_dfeatures = a->dL_dfeatures; p.accumulate = a->accumulate;
+
+    GeomState g;
+    GeomState::carve(a->geometry_buffer, p.P, &g);
+    BinState b;
+    BinState::carve(a->binning_buffer, p.R, &b);
+    ImageState im;
+    ImageState::carve(a->image_buffer, p.W, p.H, &im);
+    const uint64_t* keys_sorted;
+    const uint32_t* point_list;
+    resolve_sorted(b, p.tiles_x * p.tiles_y, keys_sorted, point_list);
+
+    rc = launch_blend_backward(p, g, point_list, im, s);
+    if (rc != GS2M_OK) return rc;
+    return launch_preprocess_backward(p, g, s);
+}
+
+int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buffer, char* binning_buffer,
+                        char* image_buffer, gs2m_state_view* out) {
+    if (!out || P < 0 || R < 0 || width <= 0 || height <= 0) { set_error("state_view: bad arguments"); return GS2M_ERR_INVALID_ARGUMENT; }
+    memset(out, 0, sizeof(*out));
+    if (geometry_buffer) {
+        GeomState g;
+        GeomState::carve(geometry_buffer, P, &g);
+        out->depths = g.depths;
+        out->rec_a = reinterpret_cast<const float*>(g.xy_conic_ab);
+        out->rec_b = reinterpret_cast<const float*>(g.conic_c_opac);
+        out->rgb = reinterpret_cast<const float*>(g.rgb);
+        out->cov3D = g.cov3D;
+        out->clamped = g.clamped;
+        out->tiles_touched = g.tiles_touched;
+        out->point_offsets = g.point_offsets;
+        out->grad_acc = g.grad_acc;
+    }
+    if (binning_buffer) {
+        BinState b;
+        BinState::carve(binning_buffer, R, &b);
+        const int tiles = ((width + GS2M_TILE_X - 1) / GS2M_TILE_X) * ((height + GS2M_TILE_Y - 1) / GS2M_TILE_Y);
+        resolve_sorted(b, tiles, out->keys_sorted, out->point_list);
+    }
+    if (image_buffer) {
+        ImageState im;
+        ImageState::carve(image_buffer, width, height, &im);
+        out->final_T = im.final_T;
+        out->n_contrib = im.n_contrib;
+        out->ranges = reinterpret_cast<const uint32_t*>(im.ranges);
+    }
+    return GS2M_OK;
+}
+
+}  // extern "C"

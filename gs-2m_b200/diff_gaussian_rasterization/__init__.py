@@ -1,0 +1,340 @@
+"""B200-native drop-in for GS-2M's ``diff_gaussian_rasterization`` package.
+
+Public surface (identical names, argument order, return tuples and gradient slots to the reference binding,
+``submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py:17-218``):
+
+* ``GaussianRasterizationSettings``  — 12-field NamedTuple (reference ``:143-155``)
+* ``GaussianRasterizer(raster_settings)(means3D, means2D, opacities, shs=, colors_precomp=, scales=, rotations=,
+  cov3D_precomp=, features=) -> (color[3,H,W], radii[P] i32, observe[P] i32, buffer[10,H,W])`` and
+  ``.markVisible(positions) -> bool[P]``  (reference ``:157-218``)
+* ``rasterize_gaussians(...)``  (reference ``:17-40``)
+
+Underneath, tensors are allocated here with torch and handed as raw device pointers to the hand-written sm_100a
+CUDA library through the C-ABI of ``include/gs2m_rasterizer.h`` (ctypes, no pybind / libtorch in the library).
+Kernels run on torch's *current stream of the inputs' device* (the reference uses the legacy default stream), so
+one-process-per-GPU data parallelism works unchanged.  There is no CPU path.
+
+Extras beyond the reference surface (used by the view-sharded data-parallel step and by the parity tests):
+``forward_raw`` / ``backward_raw`` (explicit-state calls with in-place gradient accumulation) and ``state_view``.
+"""
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from ._native import NUM_CHANNELS, NUM_FEATURES, RasterizerError  # noqa: F401
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
+           "forward_raw", "backward_raw", "state_view", "RasterizerError"]
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    feature_count: int
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# marshalling helpers
+# ----------------------------------------------------------------------------------------------------------------
+def _absent(t: Optional[torch.Tensor]) -> bool:
+    return t is None or t.numel() == 0
+
+
+def _dev_f32(t: torch.Tensor, device: torch.device, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (got %s)" % (name, t.dtype))
+    if t.device != device:
+        raise RuntimeError("%s lives on %s but means3D lives on %s" % (name, t.device, device))
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class _Arena:
+    """One growable byte buffer handed to the library through a resize callback
+    (the role of ``resizeFunctional`` in the reference glue, rasterize_points.cu:22-28)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.callback = _native.RESIZE_FN(self._resize)
+
+    def _resize(self, _user, nbytes):
+        try:
+            if self.tensor.numel() < nbytes:
+                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:  # allocation failure -> NULL -> GS2M_ERR_ALLOC
+            return None
+
+
+class RasterState(NamedTuple):
+    """What backward needs from forward (the reference keeps the same things in ``ctx``, binding ``:86-88``)."""
+    num_rendered: int
+    geom: torch.Tensor
+    binning: torch.Tensor
+    img: torch.Tensor
+
+
+def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, features,
+                raster_settings: GaussianRasterizationSettings):
+    """Run the forward pipeline. Returns ``(color, radii, observe, buffer, RasterState)``."""
+    lib = _native.load()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:52-54
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200) has no CPU path: means3D must be a CUDA tensor")
+    dev = means3D.device
+    rs = raster_settings
+    P = int(means3D.shape[0])
+    H, W = int(rs.image_height), int(rs.image_width)
+    F = int(rs.feature_count)
+
+    means3D = _dev_f32(means3D, dev, "means3D")
+    shs_t = None if _absent(shs) else _dev_f32(shs, dev, "shs")
+    col_t = None if _absent(colors_precomp) else _dev_f32(colors_precomp, dev, "colors_precomp")
+    opa_t = None if _absent(opacities) else _dev_f32(opacities, dev, "opacities")
+    sca_t = None if _absent(scales) else _dev_f32(scales, dev, "scales")
+    rot_t = None if _absent(rotations) else _dev_f32(rotations, dev, "rotations")
+    cov_t = None if _absent(cov3D_precomp) else _dev_f32(cov3D_precomp, dev, "cov3D_precomp")
+    fea_t = None if _absent(features) else _dev_f32(features, dev, "features")
+    bg = _dev_f32(rs.bg, dev, "bg")
+    vm = _dev_f32(rs.viewmatrix, dev, "viewmatrix")
+    pm = _dev_f32(rs.projmatrix, dev, "projmatrix")
+    cam = _dev_f32(rs.campos, dev, "campos")
+    if fea_t is not None and (fea_t.dim() != 2 or fea_t.shape[1] != NUM_FEATURES):
+        raise RuntimeError("features must have dimensions (num_points, %d)" % NUM_FEATURES)
+    M = int(shs_t.shape[1]) if shs_t is not None else 0
+
+    with torch.cuda.device(dev):
+        color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        buffer = torch.empty((NUM_FEATURES, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        observe = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+        a = _native.ForwardArgs()
+        a.geometry_buffer, a.binning_buffer, a.image_buffer = geom.callback, binning.callback, img.callback
+        a.P, a.D, a.M = P, int(rs.sh_degree), M
+        a.background = _ptr(bg)
+        a.width, a.height = W, H
+        a.means3D, a.shs, a.colors_precomp, a.opacities = _ptr(means3D), _ptr(shs_t), _ptr(col_t), _ptr(opa_t)
+        a.scales, a.scale_modifier, a.rotations = _ptr(sca_t), float(rs.scale_modifier), _ptr(rot_t)
+        a.cov3D_precomp, a.features = _ptr(cov_t), _ptr(fea_t)
+        a.viewmatrix, a.projmatrix, a.cam_pos = _ptr(vm), _ptr(pm), _ptr(cam)
+        a.tan_fovx, a.tan_fovy = float(rs.tanfovx), float(rs.tanfovy)
+        a.prefiltered, a.feature_count = int(bool(rs.prefiltered)), F
+        a.out_color, a.out_radii, a.out_observe, a.out_buffer = _ptr(color), _ptr(radii), _ptr(observe), _ptr(buffer)
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        num_rendered = _native.check(lib.gs2m_rasterize_forward(a), "gs2m_rasterize_forward")
+    state = RasterState(num_rendered, geom.tensor, binning.tensor, img.tensor)
+    return color, radii, observe, buffer, state
+
+
+_GRAD_SHAPES = (("dL_dmeans2D", 4), ("dL_dconic", 4), ("dL_dopacity", 1), ("dL_dcolor", 3), ("dL_dmeans3D", 3),
+                ("dL_dcov3D", 6), ("dL_dscale", 3), ("dL_drot", 4), ("dL_dfeatures", NUM_FEATURES))
+
+
+def alloc_grads(P, M, device, zero=False):
+    """Gradient tensors in the reference's shapes (rasterize_points.cu:150-159). The kernels write every element,
+    so ``torch.empty`` suffices unless the caller wants to accumulate several views (then start from zeros)."""
+    mk = torch.zeros if zero else torch.empty
+    g = {n: mk((P, c), dtype=torch.float32, device=device) for n, c in _GRAD_SHAPES}
+    g["dL_dsh"] = mk((P, M, 3), dtype=torch.float32, device=device)
+    return g
+
+
+def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features,
+                 radii, raster_settings: GaussianRasterizationSettings, state: RasterState, grads=None,
+                 accumulate=False):
+    """Run the backward pipeline into ``grads`` (dict from :func:`alloc_grads`; allocated when None).
+    With ``accumulate=True`` the nine caller-visible tensors are updated with ``+=``."""
+    lib = _native.load()
+    dev = means3D.device
+    rs = raster_settings
+    P = int(means3D.shape[0])
+    H, W = int(rs.image_height), int(rs.image_width)
+    means3D = _dev_f32(means3D, dev, "means3D")
+    shs_t = None if _absent(shs) else _dev_f32(shs, dev, "shs")
+    col_t = None if _absent(colors_precomp) else _dev_f32(colors_precomp, dev, "colors_precomp")
+    sca_t = None if _absent(scales) else _dev_f32(scales, dev, "scales")
+    rot_t = None if _absent(rotations) else _dev_f32(rotations, dev, "rotations")
+    cov_t = None if _absent(cov3D_precomp) else _dev_f32(cov3D_precomp, dev, "cov3D_precomp")
+    fea_t = None if _absent(features) else _dev_f32(features, dev, "features")
+    bg = _dev_f32(rs.bg, dev, "bg")
+    vm = _dev_f32(rs.viewmatrix, dev, "viewmatrix")
+    pm = _dev_f32(rs.projmatrix, dev, "projmatrix")
+    cam = _dev_f32(rs.campos, dev, "campos")
+    M = int(shs_t.shape[1]) if shs_t is not None else 0
+    if grad_color is None:
+        grad_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+    if grad_buffer is None:
+        grad_buffer = torch.zeros((NUM_FEATURES, H, W), dtype=torch.float32, device=dev)
+    grad_color = _dev_f32(grad_color, dev, "grad_color")
+    grad_buffer = _dev_f32(grad_buffer, dev, "grad_buffer")
+    if tuple(grad_color.shape) != (NUM_CHANNELS, H, W) or tuple(grad_buffer.shape) != (NUM_FEATURES, H, W):
+        raise RuntimeError("upstream gradients must be (3,H,W) and (10,H,W)")
+    if grads is None:
+        if accumulate:
+            raise RuntimeError("accumulate=True needs caller-provided gradient tensors")
+        grads = alloc_grads(P, M, dev)
+    if P == 0:
+        return grads
+    with torch.cuda.device(dev):
+        b = _native.BackwardArgs()
+        b.P, b.D, b.M, b.R = P, int(rs.sh_degree), M, int(state.num_rendered)
+        b.background = _ptr(bg)
+        b.width, b.height = W, H
+        b.means3D, b.shs, b.colors_precomp, b.scales = _ptr(means3D), _ptr(shs_t), _ptr(col_t), _ptr(sca_t)
+        b.scale_modifier, b.rotations, b.cov3D_precomp = float(rs.scale_modifier), _ptr(rot_t), _ptr(cov_t)
+        b.features = _ptr(fea_t)
+        b.viewmatrix, b.projmatrix, b.cam_pos = _ptr(vm), _ptr(pm), _ptr(cam)
+        b.tan_fovx, b.tan_fovy = float(rs.tanfovx), float(rs.tanfovy)
+        b.radii = _ptr(radii)
+        b.geometry_buffer, b.binning_buffer, b.image_buffer = _ptr(state.geom), _ptr(state.binning), _ptr(state.img)
+        b.geometry_bytes, b.binning_bytes, b.image_bytes = state.geom.numel(), state.binning.numel(), state.img.numel()
+        b.feature_count = int(rs.feature_count)
+        b.grad_color, b.grad_buffer = _ptr(grad_color), _ptr(grad_buffer)
+        for name, _c in _GRAD_SHAPES:
+            setattr(b, name, _ptr(grads[name]))
+        b.dL_dsh = _ptr(grads["dL_dsh"]) if M > 0 else None
+        b.accumulate = int(bool(accumulate))
+        b.stream = torch.cuda.current_stream(dev).cuda_stream
+        _native.check(lib.gs2m_rasterize_backward(b), "gs2m_rasterize_backward")
+    return grads
+
+
+def state_view(P, raster_settings, state: RasterState):
+    """Typed tensors aliasing the opaque arenas (tests only): depths, rec_a, rec_b, rgb, cov3D, clamped,
+    tiles_touched, point_offsets, grad_acc, keys_sorted, point_list, final_T, n_contrib, ranges."""
+    lib = _native.load()
+    H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+    R = int(state.num_rendered)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    v = _native.StateView()
+    _native.check(lib.gs2m_state_view_get(P, W, H, R, _ptr(state.geom) if P else None,
+                                          _ptr(state.binning) if state.binning.numel() else None,
+                                          _ptr(state.img), v), "gs2m_state_view_get")
+
+    def view(arena, ptr, count, dtype):
+        if ptr is None or count == 0:
+            return torch.empty(0, dtype=dtype, device=arena.device)
+        off = ptr - arena.data_ptr()
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return arena[off:off + nbytes].view(dtype)
+
+    out = {}
+    g, bn, im = state.geom, state.binning, state.img
+    if P:
+        out["depths"] = view(g, v.depths, P, torch.float32)
+        out["rec_a"] = view(g, v.rec_a, 4 * P, torch.float32).view(P, 4)
+        out["rec_b"] = view(g, v.rec_b, 4 * P, torch.float32).view(P, 4)
+        out["rgb"] = view(g, v.rgb, 4 * P, torch.float32).view(P, 4)
+        out["cov3D"] = view(g, v.cov3D, 6 * P, torch.float32).view(P, 6)
+        out["clamped"] = view(g, v.clamped, 4 * P, torch.uint8).view(P, 4)
+        out["tiles_touched"] = view(g, v.tiles_touched, P, torch.int32)
+        out["point_offsets"] = view(g, v.point_offsets, P, torch.int32)
+        out["grad_acc"] = view(g, v.grad_acc, _native.ACC_STRIDE * P, torch.float32).view(P, _native.ACC_STRIDE)
+    out["keys_sorted"] = view(bn, v.keys_sorted, R, torch.int64)
+    out["point_list"] = view(bn, v.point_list, R, torch.int32)
+    out["final_T"] = view(im, v.final_T, H * W, torch.float32).view(H, W)
+    out["n_contrib"] = view(im, v.n_contrib, H * W, torch.int32).view(H, W)
+    out["ranges"] = view(im, v.ranges, 2 * tiles, torch.int32).view(tiles, 2)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# autograd surface
+# ----------------------------------------------------------------------------------------------------------------
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features,
+                raster_settings):
+        color, radii, observe, buffer, state = forward_raw(
+            means3D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features, raster_settings)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = state.num_rendered
+        ctx.save_for_backward(means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp, features, radii,
+                              state.geom, state.binning, state.img)
+        ctx.mark_non_differentiable(radii, observe)
+        return color, radii, observe, buffer
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii, _grad_observe, grad_buffer):
+        (means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp, features, radii,
+         geom, binning, img) = ctx.saved_tensors
+        state = RasterState(ctx.num_rendered, geom, binning, img)
+        g = backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp,
+                         features, radii, ctx.raster_settings, state)
+        # slots: means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features, settings
+        return (g["dL_dmeans3D"], g["dL_dmeans2D"],
+                None if _absent(shs) else g["dL_dsh"],
+                None if _absent(colors_precomp) else g["dL_dcolor"],
+                g["dL_dopacity"],
+                None if _absent(scales) else g["dL_dscale"],
+                None if _absent(rotations) else g["dL_drot"],
+                None if _absent(cov3Ds_precomp) else g["dL_dcov3D"],
+                None if _absent(features) else g["dL_dfeatures"],
+                None)
+
+
+def rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, features, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """bool[P]: view-space z > 0.2 (reference ``:162-171`` -> checkFrustum, rasterizer_impl.cu:48-59)."""
+        lib = _native.load()
+        rs = self.raster_settings
+        with torch.no_grad():
+            if not positions.is_cuda:
+                raise RuntimeError("positions must be a CUDA tensor")
+            dev = positions.device
+            pos = _dev_f32(positions, dev, "positions")
+            vm = _dev_f32(rs.viewmatrix, dev, "viewmatrix")
+            pm = _dev_f32(rs.projmatrix, dev, "projmatrix")
+            P = int(pos.shape[0])
+            present = torch.zeros((P,), dtype=torch.bool, device=dev)
+            with torch.cuda.device(dev):
+                _native.check(lib.gs2m_mark_visible(P, _ptr(pos), _ptr(vm), _ptr(pm), _ptr(present),
+                                                    torch.cuda.current_stream(dev).cuda_stream), "gs2m_mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, features=None):
+        have_sh, have_col = shs is not None, colors_precomp is not None
+        if have_sh == have_col:
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        have_sr = scales is not None or rotations is not None
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (have_sr and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.Tensor([])  # CPU placeholder for absent optionals, as the reference passes (binding :192-203)
+        return rasterize_gaussians(
+            means3D, means2D,
+            shs if have_sh else empty,
+            colors_precomp if have_col else empty,
+            opacities,
+            scales if scales is not None else empty,
+            rotations if rotations is not None else empty,
+            cov3D_precomp if cov3D_precomp is not None else empty,
+            features if features is not None else empty,
+            self.raster_settings)

@@ -1,0 +1,179 @@
+/*
+ * gs2m_rasterizer.h — C-ABI of the B200-native (sm_100a) tile-based differentiable Gaussian rasterizer.
+ *
+ * Drop-in boundary for ndming/GS-2M's `submodules/diff-gaussian-rasterization`: each entry point replaces one
+ * member of the reference's native interface `CudaRasterizer::Rasterizer` (cuda_rasterizer/rasterizer.h:18-91),
+ * which the reference binds through pybind11 (ext.cpp:15-18 -> rasterize_points.cu:30-219).  Signatures use plain
+ * pointers, sizes and an opaque `cudaStream_t`; no torch / C++ types cross this boundary.  All pointers are DEVICE
+ * pointers to contiguous fp32 / int32 data unless noted; an absent optional input is NULL (the reference passes a
+ * null data_ptr for the empty CPU tensors its Python layer substitutes, diff_gaussian_rasterization/__init__.py:192-203).
+ *
+ * The three growable scratch arenas (geometry / binning / image state) are obtained through caller-supplied resize
+ * callbacks, exactly as the reference's `std::function<char*(size_t)>` arguments
+ * (cuda_rasterizer/rasterizer.h:29-31, rasterize_points.cu:22-28): the caller owns the memory, the library keeps
+ * no state between calls, and backward receives the same three blobs verbatim.  Their internal layout is private to
+ * this library (it is NOT the reference's GeometryState/BinningState/ImageState layout); `gs2m_state_view` exposes
+ * typed pointers into them for parity tests (sorted keys, tile ranges, n_contrib ...).
+ *
+ * Return value: >= 0 on success (forward: number of rendered Gaussian/tile instances R, like
+ * `Rasterizer::forward`'s return, rasterizer_impl.cu:329), negative `GS2M_ERR_*` on failure;
+ * `gs2m_last_error()` gives a message.
+ */
+#ifndef GS2M_RASTERIZER_H_
+#define GS2M_RASTERIZER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS2M_ABI_VERSION 1
+
+/* compile-time constants of the path (reference: cuda_rasterizer/config.h:15-18) */
+#define GS2M_NUM_CHANNELS 3
+#define GS2M_NUM_FEATURES 10
+#define GS2M_TILE_X 16
+#define GS2M_TILE_Y 16
+
+enum {
+    GS2M_OK = 0,
+    GS2M_ERR_INVALID_ARGUMENT = -1, /* bad sizes / missing required pointer / feature_count outside 0..10 */
+    GS2M_ERR_ALLOC = -2,            /* a resize callback returned NULL */
+    GS2M_ERR_CUDA = -3,             /* CUDA runtime error (message in gs2m_last_error) */
+    GS2M_ERR_TOO_LARGE = -4         /* instance count does not fit the 30-bit sort bookkeeping */
+};
+
+/* Resize callback: make the arena at least `bytes` long and return its (>=128-B aligned) device base pointer.
+ * Mirrors `std::function<char*(size_t N)>` of rasterizer.h:29-31. */
+typedef char* (*gs2m_resize_fn)(void* user, size_t bytes);
+
+/* ---- forward: replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:28-56, rasterizer_impl.cu:185-330) ---- */
+typedef struct gs2m_forward_args {
+    gs2m_resize_fn geometry_buffer; void* geometry_user;
+    gs2m_resize_fn binning_buffer;  void* binning_user;
+    gs2m_resize_fn image_buffer;    void* image_user;
+    int P;                    /* number of Gaussians */
+    int D;                    /* active SH degree (0..3) */
+    int M;                    /* SH coefficients per colour stored in `shs` (row stride = 3*M floats) */
+    const float* background;  /* [3] */
+    int width, height;
+    const float* means3D;       /* [P,3] */
+    const float* shs;           /* [P,M,3] or NULL */
+    const float* colors_precomp;/* [P,3]  or NULL (exactly one of shs / colors_precomp) */
+    const float* opacities;     /* [P,1] */
+    const float* scales;        /* [P,3] or NULL */
+    float scale_modifier;
+    const float* rotations;     /* [P,4] (w,x,y,z), NOT normalised by the kernels, or NULL */
+    const float* cov3D_precomp; /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
+    const float* features;      /* [P,10] side channels or NULL when feature_count == 0 */
+    const float* viewmatrix;    /* [4,4] row-major tensor of W2V^T (element (r,c) at 4*c+r) */
+    const float* projmatrix;    /* [4,4] row-major tensor of (P*W2V)^T */
+    const float* cam_pos;       /* [3] */
+    float tan_fovx, tan_fovy;
+    int prefiltered;            /* reference traps on a culled Gaussian when set; we report GS2M_ERR via debug flag only */
+    int feature_count;          /* 0..10: prefix length of `features` columns that are blended */
+    float* out_color;           /* [3,H,W]   fully written (no pre-zeroing needed) */
+    int*   out_radii;           /* [P]       fully written */
+    int*   out_observe;         /* [P]       fully written */
+    float* out_buffer;          /* [10,H,W]  fully written (channels >= feature_count are zero) */
+    void*  stream;              /* cudaStream_t */
+} gs2m_forward_args;
+
+int gs2m_rasterize_forward(const gs2m_forward_args* args);
+
+/* ---- backward: replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:58-90, rasterizer_impl.cu:334-438) ---- */
+typedef struct gs2m_backward_args {
+    int P, D, M, R;             /* R = value returned by forward */
+    const float* background;
+    int width, height;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* features;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    float tan_fovx, tan_fovy;
+    const int* radii;           /* [P] as returned by forward */
+    char* geometry_buffer;      /* the three arenas filled by forward */
+    char* binning_buffer;
+    char* image_buffer;
+    size_t geometry_bytes, binning_bytes, image_bytes;
+    int feature_count;
+    const float* grad_color;    /* dL/d out_color  [3,H,W] */
+    const float* grad_buffer;   /* dL/d out_buffer [10,H,W] (only the first feature_count planes are read) */
+    /* outputs: every element is written (culled Gaussians get zeros) unless `accumulate` is set, in which case the
+     * nine caller-visible gradient tensors are updated with += (view-sharded data parallel step: gradients of
+     * several views are summed in place before one all-reduce). */
+    float* dL_dmeans2D;         /* [P,4]  (.xy signed, .zw sum of |.|)  rasterize_points.cu:151 */
+    float* dL_dconic;           /* [P,4]  scratch-like output (x,y,-,w) rasterize_points.cu:154 */
+    float* dL_dopacity;         /* [P,1] */
+    float* dL_dcolor;           /* [P,3] */
+    float* dL_dmeans3D;         /* [P,3] */
+    float* dL_dcov3D;           /* [P,6] */
+    float* dL_dsh;              /* [P,M,3] or NULL when M == 0 */
+    float* dL_dscale;           /* [P,3] */
+    float* dL_drot;             /* [P,4] */
+    float* dL_dfeatures;        /* [P,10] */
+    int accumulate;
+    void* stream;
+} gs2m_backward_args;
+
+int gs2m_rasterize_backward(const gs2m_backward_args* args);
+
+/* Arena sizes the resize callbacks will be asked for (the `required<T>()` of rasterizer_impl.h:25-30). */
+size_t gs2m_geometry_bytes(int P);
+size_t gs2m_image_bytes(int width, int height);
+size_t gs2m_binning_bytes(int R);
+
+/* ---- markVisible: replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:21-26, rasterizer_impl.cu:132-143) ---- */
+int gs2m_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                      uint8_t* present /* [P] bool */, void* stream);
+
+/* ---- typed view into the opaque arenas (parity tests / debugging only) ---- */
+typedef struct gs2m_state_view {
+    /* geometry arena, all [P] unless noted; entries of culled Gaussians (radii == 0) are undefined */
+    const float*    depths;         /* view-space z */
+    const float*    rec_a;          /* [P,4] mean2D.x, mean2D.y, conic.x, conic.y */
+    const float*    rec_b;          /* [P,4] conic.z, opacity, 2*ln(255*opacity) footprint threshold, unused */
+    const float*    rgb;            /* [P,4] (r,g,b,unused) */
+    const float*    cov3D;          /* [P,6] */
+    const uint8_t*  clamped;        /* [P,4] (r,g,b,unused) */
+    const uint32_t* tiles_touched;
+    const uint32_t* point_offsets;  /* inclusive scan of tiles_touched */
+    const float*    grad_acc;       /* [P,24] packed backward-blend accumulator (valid after backward) */
+    /* binning arena, [R] */
+    const uint64_t* keys_sorted;    /* (tile << 32) | float_bits(depth) */
+    const uint32_t* point_list;     /* sorted Gaussian indices */
+    /* image arena */
+    const float*    final_T;        /* [H*W] */
+    const uint32_t* n_contrib;      /* [H*W] */
+    const uint32_t* ranges;         /* [tiles,2] */
+} gs2m_state_view;
+
+int gs2m_state_view_get(int P, int width, int height, int R,
+                        char* geometry_buffer, char* binning_buffer, char* image_buffer, gs2m_state_view* out);
+
+/* ---- building blocks exported on their own (parity tests of the binning stage; same device code the forward uses) ---- */
+/* Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit) — the role cub::DeviceRadixSort::SortPairs
+ * plays at rasterizer_impl.cu:291-296.  `temp` must hold gs2m_sort_temp_bytes(n) bytes. keys_in/vals_in are clobbered. */
+size_t gs2m_sort_temp_bytes(int n);
+int gs2m_sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
+                        int n, int end_bit, char* temp, void* stream);
+/* Inclusive prefix sum of u32 (cub::DeviceScan::InclusiveSum at rasterizer_impl.cu:265). temp: gs2m_scan_temp_bytes(n). */
+size_t gs2m_scan_temp_bytes(int n);
+int gs2m_inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, void* stream);
+
+const char* gs2m_last_error(void);
+int gs2m_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS2M_RASTERIZER_H_ */
