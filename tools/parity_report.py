@@ -68,7 +68,8 @@ def report(P, W, H, F, cam_radius=3.0, shell=0.0, timing=True):
         res[k] = "max/max=%.2e l2=%.2e" % (e, l2)
     # reference self-noise (float atomics): run the reference backward twice
     r2 = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
-    res["ref_self_noise_dL_dmeans2D"] = "max/max=%.2e" % helpers.grad_errors(r2["dL_dmeans2D"], r["dL_dmeans2D"])[0]
+    res["ref_self_noise"] = {k: "%.2e" % helpers.grad_errors(r2[k], r[k])[0] for k in (
+        "dL_dmeans2D", "dL_dcolor", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscale", "dL_drot", "dL_dfeatures")}
     res["list_len_mean"] = float((r["ranges"][:, 1] - r["ranges"][:, 0]).float().mean())
     res["list_len_max"] = int((r["ranges"][:, 1] - r["ranges"][:, 0]).max())
     res["n_contrib_mean"] = float(r["n_contrib"].float().mean())
