@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the rasterizer hot path: fwd+bwd views/s at 3 M Gaussians, 1959x1090, all channels (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config tnt-3m] [--views-per-rank V]
+
+A *step* is one view-sharded batch: every rank rasterizes (forward + backward, gradients accumulated in place) its
+V views of the N*V-view batch and, for N > 1, the per-Gaussian parameter gradients are summed with NCCL all-reduce.
+Per-GPU work is fixed as N grows (weak scaling).  Prints ONE JSON line (see DESIGN.md "Measurement").
+
+`--impl reference` times the unmodified reference CUDA rasterizer (compiled into oracle/_ref by oracle/build_ref.py)
+through its own Python binding on the same workload (rank 0 only; the reference has no multi-GPU path); when that
+build is absent it falls back to the CPU oracle port on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for sub in ("gs-2m_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, sub))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import synthetic_scenes as syn  # noqa: E402
+
+METRIC = "fwd+bwd views/sec @3M Gaussians 1959x1090"
+UNIT = "views/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(P, V, R, N, F, M, tiles):
+    """Compulsory HBM traffic per view, SURVEY.md section 8(d) (every input read once, every output written once,
+    every intermediate written once and read once per consuming stage)."""
+    b = {}
+    b["preprocess_fwd"] = 20 * P + V * (12 * M + 32 + 67)
+    b["scan"] = 8 * P
+    b["duplicate"] = 20 * V + 12 * R
+    b["sort"] = 24 * R
+    b["ranges"] = 8 * R + 8 * tiles
+    b["blend_fwd"] = R * (40 + 4 * F) + N * (4 * (3 + F) + 8) + 4 * P
+    b["blend_bwd"] = R * (40 + 4 * F) + N * (4 * (3 + F) + 8) + 4 * V * (12 + F)
+    b["preprocess_bwd"] = V * (12 * M + 115) + 4 * P * (34 + 3 * M)
+    b["total"] = sum(b.values())
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(cfg, n_views_total, my_views, device):
+    """Replicated scene + this rank's cameras/features, all resident on `device`."""
+    scene = syn.scene_to(syn.make_scene(cfg["P"], shell_fraction=cfg["shell"]), device)
+    cams_cpu = syn.make_cameras(n_views_total, cfg["W"], cfg["H"], radius=cfg["cam_radius"])
+    cams = {v: syn.camera_to(cams_cpu[v], device) for v in my_views}
+    feats = {v: syn.pack_features(scene, cams[v], cfg["F"]) for v in my_views}
+    gc, gb = syn.make_upstream_grads(cfg["W"], cfg["H"], cfg["F"])
+    return scene, cams_cpu, cams, feats, gc.to(device), gb.to(device)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, rank, world, device):
+    import diff_gaussian_rasterization as dgr
+    from diff_gaussian_rasterization import _native
+    import view_parallel as vp
+    lib = _native.load()
+    P, W, H, F, M = cfg["P"], cfg["W"], cfg["H"], cfg["F"], 16
+    V_per = args.views_per_rank
+    n_views = world * V_per
+    my_views = list(vp.shard_views(n_views, world, rank))
+    scene, cams_cpu, cams, feats, gc, gb = build_workload(cfg, n_views, my_views, device)
+    settings = {v: syn.raster_settings_for(cams[v], F, dgr.GaussianRasterizationSettings) for v in my_views}
+    stats = {}
+
+    def render_view(v, buckets, accumulate):
+        st = settings[v]
+        color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
+                                                               scene.scales, scene.rotations, None, feats[v], st)
+        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], radii,
+                         st, state, grads=buckets.tensors, accumulate=accumulate)
+        stats["R"], stats["radii"] = state.num_rendered, radii
+        return {"radii": radii, "observe": observe}
+
+    step = vp.ViewShardedStep(P, M, device, render_view, world=world, rank=rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        step.run(n_views)
+    barrier()
+    V_vis = int((stats["radii"] > 0).sum())
+    R = int(stats["R"])
+
+    clocks = ClockSampler(device.index)
+    if rank == 0:
+        clocks.start()
+    # ---- timed region 1: device-resident inputs ----
+    lib.gs2m_profile_enable(1)
+    _native.profile_read()
+    launches0 = lib.gs2m_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step.run(n_views)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    launches = torch.tensor([lib.gs2m_launch_count() - launches0], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    stage = _native.profile_read()
+    lib.gs2m_profile_enable(0)
+    total_ms = float(ms[0])
+    value = n_views * args.steps / (total_ms * 1e-3)
+
+    # ---- timed region 2: end to end through the public API with HOST buffers ----
+    # per view: camera + upstream-gradient images come from pinned host memory, the rendered colour image goes back.
+    pin = lambda t: t.cpu().pin_memory()  # noqa: E731
+    h_cam = {v: (pin(cams_cpu[v].world_view_transform), pin(cams_cpu[v].full_proj_transform),
+                 pin(cams_cpu[v].camera_center)) for v in my_views}
+    h_gc, h_gb = pin(gc), pin(gb)
+    h_color = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    d_gc, d_gb = torch.empty_like(gc), torch.empty_like(gb)
+    bg = torch.zeros(3, device=device)
+    h2d = sum(t.numel() * 4 for t in h_cam[my_views[0]]) + h_gc.numel() * 4 + h_gb.numel() * 4
+    d2h = h_color.numel() * 4
+
+    def render_view_e2e(v, buckets, accumulate):
+        wvt, full, cpos = (t.to(device, non_blocking=True) for t in h_cam[v])
+        d_gc.copy_(h_gc, non_blocking=True)
+        d_gb.copy_(h_gb, non_blocking=True)
+        st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, wvt, full, 3,
+                                               cpos, False, F)
+        color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
+                                                               scene.scales, scene.rotations, None, feats[v], st)
+        dgr.backward_raw(d_gc, d_gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v],
+                         radii, st, state, grads=buckets.tensors, accumulate=accumulate)
+        h_color.copy_(color, non_blocking=True)
+        return {"radii": radii, "observe": observe}
+
+    step_e2e = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank)
+    step_e2e.buckets = step.buckets
+    step_e2e.run(n_views)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e.run(n_views)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = n_views * args.steps / (float(ms2[0]) * 1e-3)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        return None
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    ab = algorithmic_bytes(P, V_vis, R, W * H, F, M, tiles)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bwd_ms, bwd_calls = stage["blend_bwd"]
+    bwd_avg_ms = bwd_ms / max(bwd_calls, 1)
+    achieved = ab["blend_bwd"] / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("blend_backward_kernel")
+    except Exception:
+        pass
+    per_view_ms = total_ms / (args.steps * V_per)
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d Gaussians, %dx%d, SH deg 3, feature_count %d (RGB+alpha+depth+normal+albedo+"
+                               "roughness+metallic), fwd+bwd, %d views per rank per step, view-sharded DP + NCCL all-reduce"
+                               % (args.config, P, W, H, F, V_per),
+                   "views_per_step": n_views, "visible_gaussians": V_vis, "instances_R": R,
+                   "l2_policy": "working set per view (%.1f GB algorithmic) exceeds the 126 MB L2; no flush needed"
+                                % (ab["total"] / 1e9)},
+        "ms_per_view": round(per_view_ms, 4),
+        "gpu_launches": int(launches[0]),
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d * V_per, "d2h_bytes_per_step": d2h * V_per,
+                "wall_ms_per_step": round(wall_ms / args.steps, 4)},
+        "roofline": {"bound": "hbm", "kernel": "blend_backward_kernel<%d>" % F, "achieved": round(achieved, 2),
+                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
+                     "algorithmic_bytes_per_launch": ab["blend_bwd"], "avg_launch_ms": round(bwd_avg_ms, 4),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "note": "blend kernels are FP32-issue/shared-memory bound, not HBM bound (DESIGN.md)"},
+        "roofline_view": {"algorithmic_bytes_per_view": ab["total"], "achieved": round(ab["total"] / (per_view_ms * 1e-3) / 1e9, 2),
+                          "frac": round(ab["total"] / (per_view_ms * 1e-3) / 1e9 / peak, 5), "unit": "GB/s"},
+        "stage_ms_per_view": {k: round(v[0] / max(v[1], 1), 4) for k, v in stage.items()},
+        "clocks": clock_info,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, args)
+    return line
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg, args, budget_tiles=None):
+    """The CPU oracle (pure-PyTorch port of the same math) timed on the host cores on a bounded sample of the same
+    workload: the full per-Gaussian stage + key sort for one view, and the blend forward+backward on an evenly spread
+    subset of tiles, scaled to the whole image (stated in `sample`; never a silent extrapolation)."""
+    import cpu_rasterizer as cr
+    import golden_io
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P, W, H, F = cfg["P"], cfg["W"], cfg["H"], cfg["F"]
+    scene = syn.make_scene(P, shell_fraction=cfg["shell"])
+    cam = syn.make_cameras(1, W, H, radius=cfg["cam_radius"])[0]
+    feats = syn.pack_features(scene, cam, F)
+    gc, gb = syn.make_upstream_grads(W, H, F)
+    settings = syn.raster_settings_for(cam, F, golden_io.Settings)
+    tiles_total = ((W + 15) // 16) * ((H + 15) // 16)
+    n_sample = budget_tiles or args.cpu_tiles
+    sample = list(range(0, tiles_total, max(1, tiles_total // n_sample)))[:n_sample]
+    orc = cr.CpuRasterizer(torch.float32)
+    t0 = time.perf_counter()
+    orc.forward(scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, feats, settings,
+                tiles=[])                       # per-Gaussian stage + duplication + sort, no blending
+    t_geom = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cr.blend_forward(orc.pre, orc.lists, orc.inp["features"], orc.bg, W, H, F, tiles=sample)
+    t_fwd = time.perf_counter() - t0
+    # backward needs the forward's per-pixel state on the sampled tiles
+    color, buffer, final_T, n_contrib, _ = cr.blend_forward(orc.pre, orc.lists, orc.inp["features"], orc.bg, W, H, F,
+                                                            tiles=sample)
+    orc.final_T, orc.n_contrib = final_T, n_contrib
+    t0 = time.perf_counter()
+    orc.backward(gc, gb, tiles=sample)          # blend backward on the sample + full per-Gaussian backward (autograd)
+    t_bwd = time.perf_counter() - t0
+    scale = tiles_total / len(sample)
+    # the per-Gaussian backward inside orc.backward is not tile-proportional; time it apart to scale only the blend
+    t0 = time.perf_counter()
+    orc.backward(gc, gb, tiles=[])
+    t_pre_bwd = time.perf_counter() - t0
+    t_view = t_geom + t_fwd * scale + (t_bwd - t_pre_bwd) * scale + t_pre_bwd
+    return {"value": round(1.0 / t_view, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle/cpu_rasterizer.py fp32, 1 view of the same workload: per-Gaussian fwd+bwd and key sort in "
+                      "full (%.1f s + %.1f s), blend fwd+bwd on %d of %d tiles (%.1f s) scaled x%.1f"
+                      % (t_geom, t_pre_bwd, len(sample), tiles_total, t_fwd + t_bwd - t_pre_bwd, scale),
+            "seconds_per_view_estimated": round(t_view, 2)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(args, cfg, rank, world, device):
+    """Reference arm: the unmodified reference rasterizer through its own binding (GaussianRasterizer + autograd)."""
+    if rank != 0:
+        return None
+    import build_ref
+    P, W, H, F = cfg["P"], cfg["W"], cfg["H"], cfg["F"]
+    V_per = args.views_per_rank
+    if not (build_ref.available() and torch.cuda.is_available()):
+        cb = cpu_baseline(cfg, args)
+        cb["kind"] = "port"
+        return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * V_per / cb["value"], 2),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s (CPU oracle port: compiled reference oracle/_ref not available)" % args.config},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    ref = build_ref.load()
+    my_views = list(range(V_per))
+    scene, cams_cpu, cams, feats, gc, gb = build_workload(cfg, V_per, my_views, device)
+    leaves = dict(means3D=scene.means3D.clone().requires_grad_(True), opacities=scene.opacities.clone().requires_grad_(True),
+                  shs=scene.shs.clone().requires_grad_(True), scales=scene.scales.clone().requires_grad_(True),
+                  rotations=scene.rotations.clone().requires_grad_(True))
+    settings = {v: syn.raster_settings_for(cams[v], F, ref.GaussianRasterizationSettings) for v in my_views}
+
+    def step():
+        for v in my_views:
+            f = feats[v].clone().requires_grad_(True)
+            m2d = torch.zeros(P, 4, device=device, requires_grad=True)
+            color, radii, observe, buffer = ref.GaussianRasterizer(settings[v])(
+                means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
+                colors_precomp=None, scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None, features=f)
+            torch.autograd.backward([color, buffer], [gc, gb])   # gradients accumulate in .grad across the views
+
+    clocks = ClockSampler(device.index)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(device)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    total_ms = e0.elapsed_time(e1)
+    value = V_per * args.steps / (total_ms * 1e-3)
+    return {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d Gaussians, %dx%d, feature_count %d, fwd+bwd, %d views per step on ONE GPU "
+                                   "(the reference has no multi-GPU path; rank 0 only)" % (args.config, P, W, H, F, V_per)},
+            "ms_per_view": round(total_ms / (args.steps * V_per), 4),
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 0, "kind": "reference",
+                             "sample": "compiled reference CUDA rasterizer (oracle/_ref, sm_100 build of the unmodified "
+                                       "sources) on the GPU through its own Python binding; full workload, no sampling"},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "clocks": clocks.stop()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="tnt-3m", choices=sorted(syn.CONFIGS))
+    ap.add_argument("--views-per-rank", type=int, default=8)
+    ap.add_argument("--cpu-tiles", type=int, default=96, help="tiles of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = syn.CONFIGS[args.config]
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.impl == "reference" and rank != 0:
+        return 0   # the reference arm runs on rank 0 alone
+    if not torch.cuda.is_available():
+        if args.impl == "reference":
+            print(json.dumps(run_reference(args, cfg, 0, 1, None)))
+            return 0
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1 and args.impl == "ours":
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    try:
+        line = run_ours(args, cfg, rank, world, device) if args.impl == "ours" else run_reference(args, cfg, rank, world, device)
+        if line is not None:
+            print(json.dumps(line))
+            sys.stdout.flush()
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

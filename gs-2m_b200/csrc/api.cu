@@ -7,6 +7,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace gs2m {
@@ -24,6 +27,28 @@ bool check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return false;
+}
+
+// ---- profiling / bookkeeping ----
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_profile{0};
+struct PendingStage { int stage; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<PendingStage> g_pending;
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+StageTimer::StageTimer(int stage, cudaStream_t s) : stage_(stage), s_(s), e0_(nullptr), e1_(nullptr), on_(false) {
+    if (!g_profile.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) return;
+    on_ = true;
+    cudaEventRecord(e0_, s_);
+}
+StageTimer::~StageTimer() {
+    if (!on_) return;
+    cudaEventRecord(e1_, s_);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_pending.push_back({stage_, e0_, e1_});
 }
 
 size_t GeomState::carve(char* base, int P, GeomState* out) {
@@ -108,6 +133,22 @@ using namespace gs2m;
 extern "C" {
 
 int gs2m_abi_version(void) { return GS2M_ABI_VERSION; }
+long long gs2m_launch_count(void) { return g_launches.load(); }
+void gs2m_profile_enable(int enable) { g_profile.store(enable ? 1 : 0); }
+int gs2m_profile_read(float* stage_ms, int* stage_calls) {
+    std::vector<PendingStage> todo;
+    { std::lock_guard<std::mutex> lk(g_prof_mu); todo.swap(g_pending); }
+    for (auto& p : todo) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            if (stage_ms) stage_ms[p.stage] += ms;
+            if (stage_calls) stage_calls[p.stage] += 1;
+        }
+        cudaEventDestroy(p.e0);
+        cudaEventDestroy(p.e1);
+    }
+    return GS2M_OK;
+}
 const char* gs2m_last_error(void) { return g_error; }
 
 size_t gs2m_geometry_bytes(int P) { return GeomState::carve(nullptr, P, nullptr); }
@@ -170,9 +211,9 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         if (!geom_base) { set_error("geometry_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
         GeomState::carve(geom_base, p.P, &g);
 
-        rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, s);
+        { StageTimer t(GS2M_STAGE_PREPROCESS_FWD, s); rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, s); }
         if (rc != GS2M_OK) return rc;
-        rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s);
+        { StageTimer t(GS2M_STAGE_SCAN, s); rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s); }
         if (rc != GS2M_OK) return rc;
         // the instance count sizes the binning arena: one device->host read, like rasterizer_impl.cu:269-270
         uint32_t r_host = 0;
@@ -189,18 +230,21 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     const uint64_t* keys_sorted = b.keys_sorted;
     point_list = b.point_list;
     if (R > 0) {
-        rc = launch_duplicate_with_keys(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, b.keys_unsorted, b.vals_unsorted, s);
+        { StageTimer t(GS2M_STAGE_DUPLICATE, s);
+          rc = launch_duplicate_with_keys(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, b.keys_unsorted, b.vals_unsorted, s); }
         if (rc != GS2M_OK) return rc;
         int in_input = 0;
-        rc = sort_pairs_u64_pingpong(b.keys_unsorted, b.keys_sorted, b.vals_unsorted, b.point_list, R,
-                                     32 + tile_bits((uint32_t)n_tiles), b.sort_temp, s, &in_input);
+        { StageTimer t(GS2M_STAGE_SORT, s);
+          rc = sort_pairs_u64_pingpong(b.keys_unsorted, b.keys_sorted, b.vals_unsorted, b.point_list, R,
+                                       32 + tile_bits((uint32_t)n_tiles), b.sort_temp, s, &in_input); }
         if (rc != GS2M_OK) return rc;
         resolve_sorted(b, n_tiles, keys_sorted, point_list);
         if ((keys_sorted == b.keys_unsorted) != (in_input != 0)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
     }
-    rc = launch_identify_tile_ranges(R, keys_sorted, im.ranges, n_tiles, s);
+    { StageTimer t(GS2M_STAGE_RANGES, s); rc = launch_identify_tile_ranges(R, keys_sorted, im.ranges, n_tiles, s); }
     if (rc != GS2M_OK) return rc;
-    rc = launch_blend_forward(p, g, point_list, im, a->out_color, a->out_observe, a->out_buffer, s);
+    { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
+      rc = launch_blend_forward(p, g, point_list, im, a->out_color, a->out_observe, a->out_buffer, s); }
     if (rc != GS2M_OK) return rc;
     return R;
 }
@@ -253,9 +297,10 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     const uint32_t* point_list;
     resolve_sorted(b, p.tiles_x * p.tiles_y, keys_sorted, point_list);
 
-    rc = launch_blend_backward(p, g, point_list, im, s);
+    { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, im, s); }
     if (rc != GS2M_OK) return rc;
-    return launch_preprocess_backward(p, g, s);
+    { StageTimer t(GS2M_STAGE_PREPROCESS_BWD, s); rc = launch_preprocess_backward(p, g, s); }
+    return rc;
 }
 
 int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buffer, char* binning_buffer,

@@ -282,6 +282,7 @@ int inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, cuda
     if (n <= 0) return GS2M_OK;
     const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t* tile_sums = reinterpret_cast<uint32_t*>(temp);
+    count_launches(3);
     scan_tile_sums_kernel<<<tiles, SCAN_THREADS, 0, s>>>(in, n, tile_sums);
     scan_spine_kernel<<<1, 1024, 0, s>>>(tile_sums, tiles);
     scan_apply_kernel<<<tiles, SCAN_THREADS, 0, s>>>(in, out, n, tile_sums);
@@ -315,6 +316,7 @@ int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* val
     GS2M_CUDA(cudaMemsetAsync(hist, 0, (size_t)((char*)(status + (size_t)passes * tiles * RS_RADIX) - (char*)hist), s));
     int hist_blocks = (n + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+    count_launches(2 + passes);
     rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys_in, n, passes, end_bit, hist);
     rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
     uint64_t* kbuf[2] = {keys_in, keys_out};
@@ -346,6 +348,7 @@ int sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uin
 int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y, uint64_t* keys,
                                uint32_t* vals, cudaStream_t s) {
     if (P == 0) return GS2M_OK;
+    count_launches(1);
     duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.xy_conic_ab, g.depths, g.point_offsets, radii, tiles_x,
                                                                tiles_y, keys, vals);
     GS2M_CUDA(cudaGetLastError());
@@ -355,6 +358,7 @@ int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int 
 int launch_identify_tile_ranges(int R, const uint64_t* keys_sorted, uint2* ranges, int n_tiles, cudaStream_t s) {
     GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)n_tiles * sizeof(uint2), s));
     if (R > 0) {
+        count_launches(1);
         identify_tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, keys_sorted, ranges);
         GS2M_CUDA(cudaGetLastError());
     }

@@ -285,6 +285,7 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
         GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    count_launches(1);
     blend_backward_kernel<F><<<grid, BLEND_THREADS, smem, s>>>(im.ranges, point_list, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                                g.conic_c_opac, g.rgb, p.features, p.background,
                                                                im.final_T, im.n_contrib, p.grad_color, p.grad_buffer,

@@ -163,6 +163,7 @@ template <int F>
 int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im, float* out_color,
              int* out_observe, float* out_buffer, cudaStream_t s) {
     dim3 grid(p.tiles_x, p.tiles_y);
+    count_launches(1);
     blend_forward_kernel<F><<<grid, BLEND_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                            g.conic_c_opac, g.rgb, p.features, p.background, im.final_T,
                                                            im.n_contrib, out_color, out_observe, out_buffer);

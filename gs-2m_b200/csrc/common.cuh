@@ -56,6 +56,12 @@ static inline void carve_array(char*& p, T*& ptr, size_t count) {
 }
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);                 // bench bookkeeping: kernels launched by this library
+struct StageTimer {                         // RAII: cudaEvent pair around one stage when profiling is enabled
+    StageTimer(int stage, cudaStream_t s);
+    ~StageTimer();
+    int stage_; cudaStream_t s_; cudaEvent_t e0_, e1_; bool on_;
+};
 bool check_cuda(cudaError_t e, const char* what);
 #define GS2M_CUDA(call) do { if (!::gs2m::check_cuda((call), #call)) return GS2M_ERR_CUDA; } while (0)
 

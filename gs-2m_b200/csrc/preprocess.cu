@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, cudaStream_t s) {
     if (p.P == 0) return GS2M_OK;
+    count_launches(1);
     preprocess_forward_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
@@ -265,6 +266,7 @@ int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii
 
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s) {
     if (P == 0) return GS2M_OK;
+    count_launches(1);
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;

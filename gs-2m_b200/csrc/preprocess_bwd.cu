@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
     if (p.P == 0) return GS2M_OK;
     const int blocks = (p.P + 255) / 256;
+    count_launches(1);
     if (p.accumulate) preprocess_backward_kernel<true><<<blocks, 256, 0, s>>>(p, g);
     else preprocess_backward_kernel<false><<<blocks, 256, 0, s>>>(p, g);
     GS2M_CUDA(cudaGetLastError());

@@ -80,7 +80,20 @@ EXPORTS = [
     ("gs2m_sort_pairs_u64", C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, C.c_void_p]),
     ("gs2m_scan_temp_bytes", C.c_size_t, [C.c_int]),
     ("gs2m_inclusive_sum_u32", C.c_int, [_fp, _fp, C.c_int, _fp, C.c_void_p]),
+    ("gs2m_profile_enable", None, [C.c_int]),
+    ("gs2m_profile_read", C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    ("gs2m_launch_count", C.c_longlong, []),
 ]
+
+STAGES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd")
+
+
+def profile_read():
+    """{stage: (total_ms, calls)} accumulated since the previous read (requires gs2m_profile_enable(1))."""
+    ms = (C.c_float * len(STAGES))()
+    calls = (C.c_int * len(STAGES))()
+    load().gs2m_profile_read(ms, calls)
+    return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(STAGES)}
 
 _lib = None
 

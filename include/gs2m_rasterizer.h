@@ -170,6 +170,20 @@ int gs2m_sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in
 size_t gs2m_scan_temp_bytes(int n);
 int gs2m_inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, void* stream);
 
+/* ---- per-stage device timing (bench.py's roofline leg) ----
+ * When enabled, forward/backward bracket every stage with cudaEvents on the launching stream.  gs2m_profile_read
+ * synchronises on the recorded events, ADDS the elapsed milliseconds and launch counts of all completed calls since
+ * the last read into the caller's arrays (indexed by the enum below) and clears the pending list.  Disabled by
+ * default (zero overhead). */
+enum {
+    GS2M_STAGE_PREPROCESS_FWD = 0, GS2M_STAGE_SCAN, GS2M_STAGE_DUPLICATE, GS2M_STAGE_SORT, GS2M_STAGE_RANGES,
+    GS2M_STAGE_BLEND_FWD, GS2M_STAGE_BLEND_BWD, GS2M_STAGE_PREPROCESS_BWD, GS2M_NUM_STAGES
+};
+void gs2m_profile_enable(int enable);
+int gs2m_profile_read(float* stage_ms /* [GS2M_NUM_STAGES] */, int* stage_calls /* [GS2M_NUM_STAGES] */);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+long long gs2m_launch_count(void);
+
 const char* gs2m_last_error(void);
 int gs2m_abi_version(void);
 

@@ -347,9 +347,16 @@ class CpuRasterizer:
         self.final_T, self.n_contrib = final_T, n_contrib
         return color, self.pre["radii"], observe, buffer
 
-    def backward(self, grad_color, grad_buffer, tiles=None):
+    def backward(self, grad_color, grad_buffer, tiles=None, final_T=None, n_contrib=None):
+        """``final_T`` / ``n_contrib`` default to this object's own forward; tests may inject the reference's saved
+        per-pixel state instead (the reference's backward reads exactly these two arrays, backward.cu:460-468) so that
+        a borderline termination decision taken differently in host floating point does not pollute the comparison."""
         dt = self.dtype
         i, s = self.inp, self.s
+        if final_T is not None:
+            self.final_T = final_T.detach().cpu().to(dt)
+        if n_contrib is not None:
+            self.n_contrib = n_contrib.detach().cpu().to(torch.int32)
         feats = i["features"] if i["features"] is not None else torch.zeros(i["means3D"].shape[0], 10, dtype=dt)
         gc, gb = grad_color.detach().cpu().to(dt), grad_buffer.detach().cpu().to(dt)
         dmean2D, dconic, dopac, dcol, dfeat = blend_backward(self.pre, self.lists, feats, self.bg, self.W, self.H,
@@ -365,7 +372,10 @@ class CpuRasterizer:
         vis = self.pre["visible"].to(dt)[:, None]
         # dL_dmeans2D.xy is already scaled by (W/2, H/2): it is the gradient w.r.t. NDC (backward.cu:490-491,378-392)
         ndc_like = torch.stack([pre["means2D"][:, 0] * (2.0 / self.W), pre["means2D"][:, 1] * (2.0 / self.H)], dim=1)
-        loss = (ndc_like * (dmean2D[:, :2] * vis)).sum() + (pre["conic"] * (dconic * vis)).sum()
+        # K5 stores HALF of dL/d(conic.y) (backward.cu:591: the off-diagonal appears twice in the symmetric matrix) and
+        # K6 doubles it again (:216-218), so the true gradient w.r.t. the packed (xx, xy, yy) conic is (g0, 2*g1, g2).
+        dconic_true = dconic * torch.tensor([1.0, 2.0, 1.0], dtype=dt)
+        loss = (ndc_like * (dmean2D[:, :2] * vis)).sum() + (pre["conic"] * (dconic_true * vis)).sum()
         if i["colors_precomp"] is None:
             loss = loss + (pre["rgb"] * (dcol * vis)).sum()
         wanted = [(k, v) for k, v in leaves.items() if v is not None]

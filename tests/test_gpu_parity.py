@@ -1,0 +1,384 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA implementation, called through the C-ABI, against
+(1) the compiled reference rasterizer (oracle/_ref) on identical seeded inputs — sort keys, sorted indices, tile
+ranges, per-pixel contributor counts, radii, observe and final transmittance BIT-EXACT; rendered channels within 1e-5
+relative; gradients within 1e-4 (max|d|/max|ref| per tensor, or 3x the reference's own run-to-run atomic noise where
+that is larger) — (2) the committed golden vectors, and (3) the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import golden_io
+import synthetic_scenes as syn
+
+pytestmark = pytest.mark.gpu
+
+GRAD_NAMES = ["dL_dmeans2D", "dL_dcolor", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscale", "dL_drot",
+              "dL_dfeatures"]
+RENDER_RTOL, RENDER_ATOL = 1e-5, 1e-7   # north_star: rendered channels within 1e-5 relative
+GRAD_TOL = 1e-4                         # north_star: gradients within 1e-4 relative (per-tensor max norm)
+
+
+@pytest.fixture(scope="module")
+def dgr():
+    import diff_gaussian_rasterization as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import build_ref
+    if not build_ref.available():
+        pytest.skip("compiled reference (oracle/_ref) not present; build with `python oracle/build_ref.py`")
+    return build_ref.load()
+
+
+def assert_forward_bit_exact(o, r, P):
+    assert o["R"] == r["R"]
+    assert torch.equal(o["radii"], r["radii"])
+    vis = r["radii"] > 0
+    assert torch.equal(o["tiles_touched"], r["tiles_touched"])
+    assert torch.equal(o["point_offsets"], r["point_offsets"])
+    for k in ("depths", "means2D", "conic_opacity", "rgb", "cov3D"):
+        assert torch.equal(helpers.bits(o[k][vis]), helpers.bits(r[k][vis])), k
+    assert torch.equal(o["clamped"].view(P, 3)[vis], r["clamped"].view(P, 3)[vis])
+    assert torch.equal(o["keys_sorted"], r["keys_sorted"])
+    assert torch.equal(o["point_list"], r["point_list"])
+    assert torch.equal(o["ranges"], r["ranges"])
+    assert torch.equal(o["n_contrib"], r["n_contrib"])
+    assert torch.equal(helpers.bits(o["final_T"]), helpers.bits(r["final_T"]))
+    assert torch.equal(o["observe"], r["observe"])
+    torch.testing.assert_close(o["color"], r["color"], rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    torch.testing.assert_close(o["buffer"], r["buffer"], rtol=RENDER_RTOL, atol=RENDER_ATOL)
+
+
+CASES = [
+    # P, W, H, F, cam_radius, shell
+    pytest.param(20_000, 320, 240, 10, 3.0, 0.7, id="20k-320x240-F10"),
+    pytest.param(100_000, 800, 800, 5, 3.0, 0.7, id="config1-100k-800x800-F5"),
+    pytest.param(300_000, 800, 600, 5, 3.0, 0.7, id="config2-300k-800x600-F5"),
+    pytest.param(500_000, 800, 800, 9, 3.0, 0.7, id="config3-500k-800x800-F9"),
+    pytest.param(500_000, 800, 800, 10, 3.0, 0.7, id="config3-500k-800x800-F10"),
+    pytest.param(3_000_000, 1959, 1090, 10, 2.2, 0.0, id="config4-3M-1959x1090-F10"),
+]
+
+
+@pytest.mark.parametrize("P,W,H,F,rad,shell", CASES)
+def test_forward_and_backward_vs_reference(dgr, ref, P, W, H, F, rad, shell):
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=shell, cam_radius=rad)
+    r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+    r2 = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)   # second run: the reference's own atomic noise
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    assert_forward_bit_exact(o, r, P)
+    for k in GRAD_NAMES:
+        err, l2 = helpers.grad_errors(o[k], r[k])
+        noise, _ = helpers.grad_errors(r2[k], r[k])
+        tol = max(GRAD_TOL, 3.0 * noise)
+        assert err <= tol, "%s: max|d|/max|ref| %.3e (l2 %.3e) > %.3e (reference self-noise %.3e)" % (k, err, l2, tol, noise)
+        assert l2 <= tol
+
+
+@pytest.mark.parametrize("F", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+def test_every_feature_count(dgr, ref, F):
+    P, W, H = 6000, 200, 136
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    if F == 0:
+        gb = torch.zeros_like(gb)
+    r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    assert_forward_bit_exact(o, r, P)
+    assert float(o["buffer"][F:].abs().max()) == 0.0 if F < 10 else True
+    for k in GRAD_NAMES:
+        err, _ = helpers.grad_errors(o[k], r[k])
+        assert err <= 5e-4, "%s F=%d err %.3e" % (k, F, err)
+    assert float(o["dL_dfeatures"][:, F:].abs().max()) == 0.0 if F < 10 else True
+
+
+@pytest.mark.parametrize("deg,M", [(0, 16), (1, 16), (2, 16), (3, 16), (1, 4), (0, 1), (2, 9)])
+def test_sh_degrees_and_coefficient_counts(dgr, ref, deg, M):
+    P, W, H, F = 4000, 160, 120, 5
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    scene = scene._replace(shs=scene.shs[:, :M].contiguous())
+    bg = torch.tensor([0.3, 0.1, 0.9], device="cuda")
+    r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb, sh_degree=deg, bg=bg)
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb, sh_degree=deg, bg=bg)
+    assert_forward_bit_exact(o, r, P)
+    for k in GRAD_NAMES:
+        err, _ = helpers.grad_errors(o[k], r[k])
+        assert err <= 5e-4, "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
+
+
+def test_precomputed_colors_and_covariances(dgr, ref):
+    """colors_precomp / cov3D_precomp inputs (binding :186-203; forward.cu:194,227; backward.cu:396,408)."""
+    P, W, H, F = 5000, 176, 144, 9
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    gen = torch.Generator().manual_seed(5)
+    colors = torch.rand(P, 3, generator=gen).cuda()
+    import cpu_rasterizer as cr
+    cov = cr._cov3d(scene.scales.cpu(), 1.0, scene.rotations.cpu()).cuda().contiguous()
+    settings = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    empty = torch.Tensor([])
+    bg = settings.bg
+    Rr, color, radii, observe, buffer, geom, binning, img = ref._C.rasterize_gaussians(
+        bg, scene.means3D, colors, scene.opacities, empty, empty, 1.0, cov, feats, cam.world_view_transform,
+        cam.full_proj_transform, cam.tanfovx, cam.tanfovy, H, W, empty, 3, cam.camera_center, False, F)
+    g_ref = ref._C.rasterize_gaussians_backward(
+        bg, scene.means3D, radii, buffer, colors, empty, empty, 1.0, cov, feats, cam.world_view_transform,
+        cam.full_proj_transform, cam.tanfovx, cam.tanfovy, gc, gb, empty, 3, cam.camera_center, geom, Rr, binning, img, F)
+    c2, radii2, obs2, buf2, state = dgr.forward_raw(scene.means3D, None, colors, scene.opacities, None, None, cov, feats,
+                                                    settings)
+    assert state.num_rendered == Rr
+    assert torch.equal(radii2, radii) and torch.equal(obs2, observe)
+    torch.testing.assert_close(c2, color, rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    torch.testing.assert_close(buf2, buffer, rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    g = dgr.backward_raw(gc, gb, scene.means3D, None, colors, None, None, cov, feats, radii2, settings, state)
+    names = ["dL_dmeans2D", "dL_dcolor", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D"]
+    for k, t in zip(names, g_ref[:5]):
+        err, _ = helpers.grad_errors(g[k], t)
+        assert err <= 5e-4, "%s err %.3e" % (k, err)
+    err, _ = helpers.grad_errors(g["dL_dfeatures"], g_ref[8])
+    assert err <= 5e-4
+    assert float(g["dL_dscale"].abs().max()) == 0.0 and float(g["dL_drot"].abs().max()) == 0.0
+
+
+def test_autograd_surface_matches_reference_binding(dgr, ref):
+    """GaussianRasterizer(...)(...) + loss.backward() through both Python bindings (same call render() makes,
+    gaussian_renderer/__init__.py:98-123)."""
+    P, W, H, F = 8000, 240, 160, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+
+    def run(mod):
+        leaves = dict(means3D=scene.means3D.clone().requires_grad_(True),
+                      means2D=torch.zeros(P, 4, device="cuda", requires_grad=True),
+                      opacities=scene.opacities.clone().requires_grad_(True),
+                      shs=scene.shs.clone().requires_grad_(True), scales=scene.scales.clone().requires_grad_(True),
+                      rotations=scene.rotations.clone().requires_grad_(True), features=feats.clone().requires_grad_(True))
+        settings = syn.raster_settings_for(cam, F, mod.GaussianRasterizationSettings)
+        rast = mod.GaussianRasterizer(raster_settings=settings)
+        color, radii, observe, buffer = rast(means3D=leaves["means3D"], means2D=leaves["means2D"],
+                                            opacities=leaves["opacities"], shs=leaves["shs"], colors_precomp=None,
+                                            scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None,
+                                            features=leaves["features"])
+        loss = (color * gc).sum() + (buffer * gb).sum()
+        loss.backward()
+        return color, radii, observe, buffer, {k: v.grad for k, v in leaves.items()}
+
+    c1, r1, o1, b1, g1 = run(ref)
+    c2, r2, o2, b2, g2 = run(dgr)
+    assert c2.shape == (3, H, W) and b2.shape == (10, H, W) and r2.dtype == torch.int32 and o2.dtype == torch.int32
+    assert torch.equal(r1, r2) and torch.equal(o1, o2)
+    torch.testing.assert_close(c2, c1, rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    torch.testing.assert_close(b2, b1, rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    for k in g1:
+        assert g2[k] is not None and g2[k].shape == g1[k].shape, k
+        err, _ = helpers.grad_errors(g2[k], g1[k])
+        assert err <= 5e-4, "%s err %.3e" % (k, err)
+
+
+def test_mark_visible(dgr, ref):
+    scene, cam, feats, _, _ = helpers.make_view(50_000, 320, 240, 1, cam_radius=0.5)   # camera inside the cloud
+    settings = syn.raster_settings_for(cam, 1, dgr.GaussianRasterizationSettings)
+    ours = dgr.GaussianRasterizer(settings).markVisible(scene.means3D)
+    theirs = ref._C.mark_visible(scene.means3D, cam.world_view_transform, cam.full_proj_transform)
+    assert ours.dtype == torch.bool and torch.equal(ours, theirs)
+    assert 0 < int(ours.sum()) < 50_000
+
+
+def test_input_validation_mirrors_reference(dgr):
+    scene, cam, feats, _, _ = helpers.make_view(100, 64, 64, 5)
+    settings = syn.raster_settings_for(cam, 5, dgr.GaussianRasterizationSettings)
+    rast = dgr.GaussianRasterizer(settings)
+    m2d = torch.zeros(100, 4, device="cuda")
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        rast(scene.means3D, m2d, scene.opacities, shs=None, colors_precomp=None, scales=scene.scales, rotations=scene.rotations)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        rast(scene.means3D, m2d, scene.opacities, shs=scene.shs, scales=scene.scales, rotations=None)
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        rast(scene.means3D.view(-1), m2d, scene.opacities, shs=scene.shs, scales=scene.scales, rotations=scene.rotations)
+    with pytest.raises(dgr.RasterizerError):   # feature_count outside 0..10 is rejected by the C-ABI, not UB
+        bad = settings._replace(feature_count=11)
+        dgr.GaussianRasterizer(bad)(scene.means3D, m2d, scene.opacities, shs=scene.shs, scales=scene.scales,
+                                    rotations=scene.rotations, features=feats)
+
+
+def test_empty_and_fully_culled_inputs(dgr, ref):
+    """P == 0 short-circuit (rasterize_points.cu:78,161) and a view that culls everything (ranges stay (0,0))."""
+    scene, cam, feats, gc, gb = helpers.make_view(1000, 100, 70, 5)
+    settings = syn.raster_settings_for(cam, 5, dgr.GaussianRasterizationSettings,
+                                       bg=torch.tensor([0.25, 0.5, 0.75], device="cuda"))
+    z = lambda *s: torch.zeros(*s, device="cuda")  # noqa: E731
+    color, radii, observe, buffer, state = dgr.forward_raw(z(0, 3), z(0, 16, 3), None, z(0, 1), z(0, 3), z(0, 4), None,
+                                                           z(0, 10), settings)
+    assert state.num_rendered == 0 and radii.numel() == 0
+    assert torch.equal(color, settings.bg[:, None, None].expand(3, 70, 100))
+    assert float(buffer.abs().max()) == 0.0
+    # everything behind the camera
+    behind = scene._replace(means3D=(scene.means3D * 0.01 + cam.camera_center[None] * 3.0).contiguous())
+    o = helpers.run_ours(dgr, behind, cam, feats, 5, gc, gb, bg=settings.bg)
+    r = helpers.run_reference(ref, behind, cam, feats, 5, gc, gb, bg=settings.bg)
+    assert o["R"] == 0 and r["R"] == 0
+    assert int(o["radii"].abs().sum()) == 0 and int(o["ranges"].abs().sum()) == 0
+    torch.testing.assert_close(o["color"], r["color"], rtol=0, atol=0)
+    for k in GRAD_NAMES:
+        assert float(o[k].abs().max()) == 0.0, k
+
+
+def test_huge_and_degenerate_gaussians(dgr, ref):
+    """Screen-filling splats (long per-tile lists, every tile touched), needle-like splats and opacity below 1/255."""
+    P, W, H, F = 3000, 330, 210, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.5)
+    scales = scene.scales.clone()
+    scales[:40] *= 80.0                        # screen filling
+    scales[40:400, 0] *= 30.0                  # needles
+    scales[400:500] *= 1e-3                    # sub-pixel (radius clamps through the 0.1 floor)
+    opac = scene.opacities.clone()
+    opac[500:700] = 0.003                      # can never reach alpha 1/255
+    opac[700:800] = 1.0
+    scene = scene._replace(scales=scales.contiguous(), opacities=opac.contiguous())
+    r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    assert_forward_bit_exact(o, r, P)
+    r2 = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+    for k in GRAD_NAMES:
+        err, _ = helpers.grad_errors(o[k], r[k])
+        noise, _ = helpers.grad_errors(r2[k], r[k])
+        assert err <= max(5e-4, 3 * noise), "%s err %.3e noise %.3e" % (k, err, noise)
+
+
+@pytest.mark.parametrize("path", golden_io.golden_files(), ids=[p.split("/")[-1] for p in golden_io.golden_files()])
+def test_against_golden_vectors(dgr, path):
+    """Committed outputs of the compiled reference (tests/golden): needs no reference on the box."""
+    inp, gold = golden_io.load(path, device="cuda", settings_cls=dgr.GaussianRasterizationSettings)
+    s = inp["scene"]
+    color, radii, observe, buffer, state = dgr.forward_raw(s.means3D, s.shs, None, s.opacities, s.scales, s.rotations,
+                                                           None, inp["features"], inp["settings"])
+    sv = dgr.state_view(inp["P"], inp["settings"], state)
+    assert state.num_rendered == int(gold["R"][0])
+    for name, mine in (("radii", radii), ("observe", observe), ("keys_sorted", sv["keys_sorted"]),
+                       ("point_list", sv["point_list"]), ("ranges", sv["ranges"]), ("n_contrib", sv["n_contrib"])):
+        assert torch.equal(mine.cpu(), gold[name]), name
+    assert torch.equal(helpers.bits(sv["final_T"]).cpu(), helpers.bits(gold["final_T"]))
+    torch.testing.assert_close(color.cpu(), gold["color"], rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    torch.testing.assert_close(buffer.cpu(), gold["buffer"], rtol=RENDER_RTOL, atol=RENDER_ATOL)
+    g = dgr.backward_raw(inp["grad_color"], inp["grad_buffer"], s.means3D, s.shs, None, s.scales, s.rotations, None,
+                         inp["features"], radii, inp["settings"], state)
+    for k in GRAD_NAMES:
+        err, _ = helpers.grad_errors(g[k].cpu(), gold[k])
+        assert err <= 5e-4, "%s err %.3e" % (k, err)
+
+
+def test_against_cpu_oracle(dgr):
+    """CUDA path vs the pure-PyTorch CPU restatement on a small seeded scene (the check smoke() also runs)."""
+    import cpu_rasterizer as cr
+    P, W, H, F = 3000, 128, 96, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.7)
+    settings = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    orc = cr.CpuRasterizer(torch.float64)
+    color, radii, observe, buffer = orc.forward(scene.means3D, scene.shs, None, scene.opacities, scene.scales,
+                                                scene.rotations, None, feats, settings)
+    assert (radii != o["radii"].cpu()).sum().item() <= 3
+    torch.testing.assert_close(o["color"].cpu().double(), color, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(o["buffer"].cpu().double(), buffer, rtol=1e-4, atol=2e-5)
+    g = orc.backward(gc, gb, final_T=o["final_T"], n_contrib=o["n_contrib"])
+    for k in GRAD_NAMES:
+        err, _ = helpers.grad_errors(o[k].cpu(), g[k])
+        tol = 5e-4 if k in ("dL_dcov3D", "dL_dscale", "dL_drot") else 1e-4
+        assert err <= tol, "%s err %.3e" % (k, err)
+
+
+def test_full_size_properties(dgr):
+    """Size-independent properties at BASELINE config 4 (3 M Gaussians, 1959x1090, F=10), no reference needed."""
+    cfg = syn.CONFIGS["tnt-3m"]
+    P, W, H, F = cfg["P"], cfg["W"], cfg["H"], cfg["F"]
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=cfg["shell"], cam_radius=cfg["cam_radius"])
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    keys = o["keys_sorted"]
+    R = o["R"]
+    assert R > P // 2
+    # sortedness (keys are positive: tile < 2^14, depth > 0) and tie-break by ascending Gaussian index
+    assert bool((keys[1:] >= keys[:-1]).all())
+    ties = keys[1:] == keys[:-1]
+    assert bool((o["point_list"][1:][ties] > o["point_list"][:-1][ties]).all())
+    # the sorted list is a permutation of the emitted instances: per-Gaussian counts match tiles_touched
+    counts = torch.bincount(o["point_list"].long(), minlength=P)
+    assert torch.equal(counts.int(), o["tiles_touched"])
+    # ranges partition [0,R) by tile id
+    rg = o["ranges"].long()
+    lens = rg[:, 1] - rg[:, 0]
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    tile_of = (keys >> 32)
+    nz = torch.nonzero(lens > 0).reshape(-1)
+    assert torch.equal(tile_of[rg[nz, 0]], nz) and torch.equal(tile_of[rg[nz, 1] - 1], nz)
+    # depth part of every key is the Gaussian's depth bits
+    depth_bits = o["depths"].view(torch.int32).long()[o["point_list"].long()]
+    assert torch.equal(keys & 0xFFFFFFFF, depth_bits)
+    # determinism of the forward (idempotence): bit-identical on a second run
+    o2 = helpers.run_ours(dgr, scene, cam, feats, F)
+    for k in ("color", "buffer", "n_contrib", "observe", "radii", "point_list"):
+        assert torch.equal(helpers.bits(o[k]), helpers.bits(o2[k])), k
+    # alpha channel of the buffer equals 1 - final_T (features[:,0] == 1, no background on features)
+    torch.testing.assert_close(o["buffer"][0], 1.0 - o["final_T"], rtol=0, atol=2e-5)
+    # linearity of the backward in the upstream gradient, and accumulate mode == sum of two backward passes
+    settings = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    c, radii, obs, buf, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities, scene.scales,
+                                                scene.rotations, None, feats, settings)
+    args = (scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats, radii, settings, state)
+    g1 = dgr.backward_raw(gc, gb, *args)
+    g2 = dgr.backward_raw(2.0 * gc, 2.0 * gb, *args)
+    acc = dgr.alloc_grads(P, 16, "cuda", zero=True)
+    dgr.backward_raw(gc, gb, *args, grads=acc, accumulate=True)
+    dgr.backward_raw(gc, gb, *args, grads=acc, accumulate=True)
+    for k in GRAD_NAMES:
+        e, _ = helpers.grad_errors(g2[k], 2.0 * g1[k])
+        assert e <= 1e-4, "linearity %s %.3e" % (k, e)
+        e, _ = helpers.grad_errors(acc[k], 2.0 * g1[k])
+        assert e <= 1e-4, "accumulate %s %.3e" % (k, e)
+    # culled Gaussians receive exactly zero gradient
+    culled = o["radii"] == 0
+    assert int(culled.sum()) > 0
+    for k in GRAD_NAMES:
+        assert float(g1[k][culled].abs().max()) == 0.0, k
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 3071, 3072, 3073, 100_000, 2_000_003])
+@pytest.mark.parametrize("end_bit", [9, 32, 46, 64])
+def test_radix_sort_building_block(dgr, n, end_bit):
+    """gs2m_sort_pairs_u64 against numpy's stable argsort on the masked key bits (what SortPairs does at
+    rasterizer_impl.cu:291-296)."""
+    from diff_gaussian_rasterization import _native
+    lib = _native.load()
+    rng = np.random.default_rng(n * 131 + end_bit)
+    keys = rng.integers(0, 2 ** 63, size=n, dtype=np.int64)
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]   # plenty of duplicates: stability matters
+        rng.shuffle(keys[: n // 2])
+    vals = np.arange(n, dtype=np.int32)
+    k_in = torch.from_numpy(keys).cuda()
+    v_in = torch.from_numpy(vals).cuda()
+    k_out, v_out = torch.empty_like(k_in), torch.empty_like(v_in)
+    temp = torch.empty(lib.gs2m_sort_temp_bytes(n), dtype=torch.uint8, device="cuda")
+    p = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+    rc = lib.gs2m_sort_pairs_u64(p(k_in), p(k_out), p(v_in), p(v_out), n, end_bit, temp.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ku = keys.view(np.uint64)
+    masked = ku & np.uint64((1 << end_bit) - 1) if end_bit < 64 else ku
+    order = np.argsort(masked, kind="stable")
+    assert np.array_equal(v_out.cpu().numpy(), vals[order])
+    assert np.array_equal(k_out.cpu().numpy().view(np.uint64), ku[order])
+
+
+@pytest.mark.parametrize("n", [1, 255, 2048, 2049, 1_000_003, 6_000_000])
+def test_inclusive_scan_building_block(dgr, n):
+    from diff_gaussian_rasterization import _native
+    lib = _native.load()
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 40, size=n, dtype=np.int32)
+    xin = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xin)
+    temp = torch.empty(lib.gs2m_scan_temp_bytes(n), dtype=torch.uint8, device="cuda")
+    assert lib.gs2m_inclusive_sum_u32(xin.data_ptr(), out.data_ptr(), n, temp.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream) == 0
+    assert np.array_equal(out.cpu().numpy(), np.cumsum(x, dtype=np.int64).astype(np.int32))
