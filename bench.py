@@ -162,28 +162,55 @@ def run_ours(args, cfg, rank, world, device):
     value = n_views * args.steps / (total_ms * 1e-3)
 
     # ---- timed region 2: end to end through the public API with HOST buffers ----
-    # per view: camera + upstream-gradient images come from pinned host memory, the rendered colour image goes back.
+    # What lives on the host in GS-2M's training loop is the camera and its ground-truth image; every view therefore
+    # copies (pinned host -> device) its camera matrices and a GT image, renders, turns the GT image into dL/dcolor
+    # on the device (L2 photometric loss, the caller's job), runs the backward, and reads the loss back to the host.
+    # dL/dbuffer (regularisers on the feature planes) is produced on the device in the real loop and stays resident.
+    # The next view's host->device copies are issued on a side stream so they overlap the current view's kernels.
     pin = lambda t: t.cpu().pin_memory()  # noqa: E731
     h_cam = {v: (pin(cams_cpu[v].world_view_transform), pin(cams_cpu[v].full_proj_transform),
                  pin(cams_cpu[v].camera_center)) for v in my_views}
-    h_gc, h_gb = pin(gc), pin(gb)
-    h_color = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-    d_gc, d_gb = torch.empty_like(gc), torch.empty_like(gb)
+    gen = torch.Generator().manual_seed(7)
+    h_gt = torch.rand((3, H, W), generator=gen).pin_memory()
+    h_loss = torch.zeros(len(my_views), dtype=torch.float32).pin_memory()
     bg = torch.zeros(3, device=device)
-    h2d = sum(t.numel() * 4 for t in h_cam[my_views[0]]) + h_gc.numel() * 4 + h_gb.numel() * 4
-    d2h = h_color.numel() * 4
+    copy_stream = torch.cuda.Stream(device=device)
+    slots = [dict(gt=torch.empty((3, H, W), device=device), wvt=torch.empty((4, 4), device=device),
+                  full=torch.empty((4, 4), device=device), cpos=torch.empty(3, device=device),
+                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    h2d = sum(t.numel() * 4 for t in h_cam[my_views[0]]) + h_gt.numel() * 4
+    d2h = 4
+    seq = {"k": 0}
+
+    def prefetch(k, v):
+        sl = slots[k % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl["free"])
+            sl["gt"].copy_(h_gt, non_blocking=True)
+            sl["wvt"].copy_(h_cam[v][0], non_blocking=True)
+            sl["full"].copy_(h_cam[v][1], non_blocking=True)
+            sl["cpos"].copy_(h_cam[v][2], non_blocking=True)
+            sl["ready"].record(copy_stream)
 
     def render_view_e2e(v, buckets, accumulate):
-        wvt, full, cpos = (t.to(device, non_blocking=True) for t in h_cam[v])
-        d_gc.copy_(h_gc, non_blocking=True)
-        d_gb.copy_(h_gb, non_blocking=True)
-        st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, wvt, full, 3,
-                                               cpos, False, F)
+        k = seq["k"]
+        if k == 0:
+            prefetch(0, v)
+        pos = my_views.index(v)
+        prefetch(k + 1, my_views[(pos + 1) % len(my_views)])
+        sl = slots[k % 2]
+        torch.cuda.current_stream(device).wait_event(sl["ready"])
+        st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, sl["wvt"],
+                                               sl["full"], 3, sl["cpos"], False, F)
         color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
                                                                scene.scales, scene.rotations, None, feats[v], st)
-        dgr.backward_raw(d_gc, d_gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v],
+        diff = color - sl["gt"]
+        h_loss[pos].copy_((diff * diff).mean(), non_blocking=True)
+        grad_c = diff * (2.0 / diff.numel())
+        dgr.backward_raw(grad_c, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v],
                          radii, st, state, grads=buckets.tensors, accumulate=accumulate)
-        h_color.copy_(color, non_blocking=True)
+        sl["free"].record(torch.cuda.current_stream(device))
+        seq["k"] = k + 1
         return {"radii": radii, "observe": observe}
 
     step_e2e = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank)

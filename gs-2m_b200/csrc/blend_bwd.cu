@@ -3,66 +3,67 @@
 //
 // Behavioural reference: renderCUDA backward (cuda_rasterizer/backward.cu:413-598), which issues 11+F same-address
 // float atomics per (pixel, Gaussian) pair.  This kernel produces the same sums (to fp32 re-association) with
-// *no per-pixel atomics*:
+// *no per-pixel atomics* and *no block-wide barriers in the main loop*:
 //
-//   evaluate (lane = pixel)   For a list entry whose footprint reaches the warp's 8x4 block, every lane recomputes
-//                             alpha bit-exactly like the forward, steps T <- T/(1-alpha), and needs only two scalars
-//                             per pair:  w = alpha*T  (weight of the colour/feature gradients) and
-//                             Q = G * dL/dalpha       (weight of every geometric gradient).
+//   warp-autonomous walk      A CTA is one 16x16 tile, but each of its 8 warps owns an 8x4 pixel block and walks the
+//                             tile's list on its own, 32 entries per step: lane l gathers the 32-byte blend record of
+//                             entry l (the 8 warps of a tile read the same records at about the same time, so these
+//                             hit in L1), proves with the conservative footprint test whether the entry can reach
+//                             the warp's pixel block, and the ballot of those tests is the warp's work list.  Entries
+//                             behind the warp's deepest last-contributor are never touched.  (The round-1 first cut
+//                             staged batches per CTA behind __syncthreads; ncu showed 32% of the stall samples on
+//                             those barriers because the 8 warps of a tile have very unequal work.)
+//   evaluate (lane = pixel)   For a surviving entry every lane recomputes alpha bit-exactly like the forward, steps
+//                             T <- T/(1-alpha), and needs only two scalars per pair:  w = alpha*T  (weight of the
+//                             colour/feature gradients) and  Q = G * dL/dalpha  (weight of every geometric gradient).
 //                             dL/dalpha uses the scalar recurrence  S <- a_prev*cd_prev + (1-a_prev)*S  with
 //                             cd = <colour+features, dL/dpixel>, algebraically identical to the reference's
 //                             per-channel accum_rec/accum_buf recurrences (backward.cu:546-560).
 //                             (w, Q) of 32 pixels x up to 32 entries are parked in a per-warp shared tile.
 //   reduce (lane = Gaussian)  When 32 entries are parked the warp transposes roles: lane g owns entry g and sums
 //                             over the 32 pixels — 3+F colour/feature sums and 8 geometric moments — privately in
-//                             registers.  This is the "warp-aggregated accumulation": a shared-memory transpose
-//                             instead of 21 shuffle butterflies per pair.
-//   accumulate                Lane g adds its 11+F sums into a per-CTA shared accumulator row of its list entry
-//                             (8 warps share a row), and after the batch one thread per entry issues the 11+F
-//                             global atomics: one set per (Gaussian, tile) instead of per (Gaussian, pixel).
-//
-// Entries behind every pixel's last contributor are never staged (the reference stages and skips them), and the
-// same conservative footprint masks as in the forward keep warps away from entries that cannot touch them.
+//                             registers: a shared-memory transpose instead of 21 shuffle butterflies per pair.
+//   accumulate                Lane g adds its 11+F sums to the Gaussian's packed 96-byte accumulator row with
+//                             128-bit vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4): 6 per
+//                             (Gaussian, warp block) instead of 21 x 32 scalar atomics.
 #include "blend_common.cuh"
 
 namespace gs2m {
 namespace {
 
-constexpr int BWD_BATCH = 128;   // list entries staged per round
 constexpr int PARK = 32;         // entries parked per warp before a reduce
 constexpr int PARK_STRIDE = 33;  // padded row -> conflict-free for both write (lane = pixel) and read (lane = entry)
 
 template <int F>
-struct BwdSmem {
+struct WarpSmemB {
     static constexpr int NV = (3 + F + 3) / 4;
-    static constexpr int NG = 11 + F;                       // gradient sums per Gaussian
-    float4 a[BWD_BATCH];
-    float4 b[BWD_BATCH];
-    float4 col[NV][BWD_BATCH];
-    float4 dpix[BLEND_WARPS][32][NV];                       // dL/d(colour,features) of every pixel, per warp
-    float park_w[BLEND_WARPS][PARK * PARK_STRIDE];
-    float park_q[BLEND_WARPS][PARK * PARK_STRIDE];
-    float acc[BWD_BATCH][NG];
-    uint32_t words[BLEND_WARPS][BWD_BATCH / 32];
-    uint32_t warp_max[BLEND_WARPS];
-    uint32_t touched[BWD_BATCH / 32];
+    float4 a[32];                  // staged records of the current 32-entry step
+    float4 b[32];
+    float4 col[NV][32];
+    float4 dpix[32][NV];           // dL/d(colour,features) of the warp's 32 pixels
+    float park_w[PARK * PARK_STRIDE];
+    float park_q[PARK * PARK_STRIDE];
 };
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int F>
-__device__ __forceinline__ void reduce_parked(BwdSmem<F>& sm, int warp, int lane, int n_parked, int my_slot, float wpx0,
-                                              float wpy0, float half_w, float half_h) {
-    constexpr int NV = BwdSmem<F>::NV;
+__device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_parked, float4 ra, float2 rb, int gid,
+                                              float wpx0, float wpy0, float half_w, float half_h,
+                                              float* __restrict__ grad_acc) {
+    constexpr int NV = WarpSmemB<F>::NV;
     constexpr int NC = 3 + F;
+    constexpr int NG = 11 + F;
     if (lane < n_parked) {
-        const float4 ra = sm.a[my_slot];
-        const float4 rb = sm.b[my_slot];
         const float gx = ra.x, gy = ra.y, ca = ra.z, cb = ra.w, cc = rb.x, op = rb.y;
         float gc[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) gc[i] = 0.f;
         float sx = 0.f, sy = 0.f, ax = 0.f, ay = 0.f, cxx = 0.f, cxy = 0.f, cyy = 0.f, so = 0.f;
-        const float* pw = &sm.park_w[warp][lane * PARK_STRIDE];
-        const float* pq = &sm.park_q[warp][lane * PARK_STRIDE];
+        const float* pw = &sm.park_w[lane * PARK_STRIDE];
+        const float* pq = &sm.park_q[lane * PARK_STRIDE];
 #pragma unroll 8
         for (int p = 0; p < 32; ++p) {
             const float w = pw[p];
@@ -70,7 +71,7 @@ __device__ __forceinline__ void reduce_parked(BwdSmem<F>& sm, int warp, int lane
             float d[4 * NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                const float4 t = sm.dpix[warp][p][k];
+                const float4 t = sm.dpix[p][k];
                 d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
             }
 #pragma unroll
@@ -86,18 +87,23 @@ __device__ __forceinline__ void reduce_parked(BwdSmem<F>& sm, int warp, int lane
             cyy = fmaf(qdy, dy, cyy);
             so += q;
         }
-        float* acc = sm.acc[my_slot];
-        const float kx = op * half_w, ky = op * half_h;
-        atomicAdd(acc + 0, -kx * sx);
-        atomicAdd(acc + 1, -ky * sy);
-        atomicAdd(acc + 2, fabsf(kx) * ax);
-        atomicAdd(acc + 3, fabsf(ky) * ay);
-        atomicAdd(acc + 4, -0.5f * op * cxx);
-        atomicAdd(acc + 5, -0.5f * op * cxy);
-        atomicAdd(acc + 6, -0.5f * op * cyy);
-        atomicAdd(acc + 7, so);
+        float out[GS2M_ACC_STRIDE];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) atomicAdd(acc + 8 + i, gc[i]);
+        for (int i = 0; i < GS2M_ACC_STRIDE; ++i) out[i] = 0.f;
+        const float kx = op * half_w, ky = op * half_h;
+        out[0] = -kx * sx;
+        out[1] = -ky * sy;
+        out[2] = fabsf(kx) * ax;
+        out[3] = fabsf(ky) * ay;
+        out[4] = -0.5f * op * cxx;
+        out[5] = -0.5f * op * cxy;
+        out[6] = -0.5f * op * cyy;
+        out[7] = so;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) out[8 + i] = gc[i];
+        float* dst = grad_acc + (size_t)gid * GS2M_ACC_STRIDE;
+#pragma unroll
+        for (int v = 0; v < (NG + 3) / 4; ++v) red_add_v4(dst + 4 * v, out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
     }
     __syncwarp();
 }
@@ -110,12 +116,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ grad_color, const float* __restrict__ grad_buffer,
     float* __restrict__ grad_acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem<F>& sm = *reinterpret_cast<BwdSmem<F>*>(smem_raw);
-    constexpr int NV = BwdSmem<F>::NV;
+    constexpr int NV = WarpSmemB<F>::NV;
     constexpr int NC = 3 + F;
-    constexpr int NG = BwdSmem<F>::NG;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpSmemB<F>& sm = reinterpret_cast<WarpSmemB<F>*>(smem_raw)[warp];
     const int tile_x = blockIdx.x, tile_y = blockIdx.y;
     int px, py;
     pixel_of_thread(tile_x, tile_y, tid, px, py);
@@ -142,144 +147,115 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(
     }
     const float bg_dot = bg[0] * dL[0] + bg[1] * dL[1] + bg[2] * dL[2];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) sm.dpix[warp][lane][k] = make_float4(dL[4 * k], dL[4 * k + 1], dL[4 * k + 2], dL[4 * k + 3]);
+    for (int k = 0; k < NV; ++k) sm.dpix[lane][k] = make_float4(dL[4 * k], dL[4 * k + 1], dL[4 * k + 2], dL[4 * k + 3]);
 
-    // deepest contributor of this warp / of the tile: nothing behind it is ever staged
+    // deepest contributor of this warp: nothing behind it is ever touched
     uint32_t wmax = my_contrib;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) sm.warp_max[warp] = wmax;
-    __syncthreads();
-    uint32_t tile_max = 0;
-#pragma unroll
-    for (int w = 0; w < BLEND_WARPS; ++w) tile_max = max(tile_max, sm.warp_max[w]);
-    if (tile_max > (uint32_t)n_list) tile_max = (uint32_t)n_list;  // defensive; forward guarantees <=
-    const int n_back = (int)tile_max;                                // entries [0, n_back) in forward order matter
-    const int rounds = (n_back + BWD_BATCH - 1) / BWD_BATCH;
+    const int n_back = (int)min(wmax, (uint32_t)n_list);   // forward guarantees wmax <= n_list; defensive
+    __syncwarp();
 
-    const float wpx0 = (float)(tile_x * GS2M_TILE_X + (warp & 1) * WARP_PIX_X);
-    const float wpy0 = (float)(tile_y * GS2M_TILE_Y + (warp >> 1) * WARP_PIX_Y);
+    const int wpx0i = tile_x * GS2M_TILE_X + (warp & 1) * WARP_PIX_X;
+    const int wpy0i = tile_y * GS2M_TILE_Y + (warp >> 1) * WARP_PIX_Y;
+    const float wpx0 = (float)wpx0i, wpy0 = (float)wpy0i;
     const float half_w = 0.5f * (float)W, half_h = 0.5f * (float)H;
 
     float S = 0.f, last_alpha = 0.f, last_cd = 0.f;
-    int n_parked = 0, my_slot = 0;
+    int n_parked = 0, my_gid = 0;
+    float4 my_ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 my_rb = make_float2(0.f, 0.f);
 
-    for (int batch = 0; batch < rounds; ++batch) {
-        // ---- stage entries f = n_back-1-(batch*BATCH+t), t < BATCH, in back-to-front order ----
-        uint32_t mask = 0;
-        int staged_id = -1;
-        if (tid < BWD_BATCH) {
-            const int f = n_back - 1 - (batch * BWD_BATCH + tid);
-            if (f >= 0) {
-                staged_id = (int)point_list[range.x + f];
-                const float4 ra = __ldg(rec_a + staged_id);
-                const float4 rb = __ldg(rec_b + staged_id);
-                const CullRecord cr = make_cull_record(ra, rb);
-                mask = warp_block_mask(cr, tile_x * GS2M_TILE_X, tile_y * GS2M_TILE_Y);
+    for (int base = 0; base < n_back; base += 32) {
+        // ---- lane l looks at entry f = n_back-1-(base+l): back-to-front, lane 0 deepest ----
+        const int f = n_back - 1 - (base + lane);
+        bool hit = false;
+        int gid = 0;
+        if (f >= 0) {
+            gid = (int)point_list[range.x + f];
+            const float4 ra = __ldg(rec_a + gid);
+            const float4 rb = __ldg(rec_b + gid);
+            const CullRecord cr = make_cull_record(ra, rb);
+            hit = rect_may_contribute(cr, wpx0, wpy0, wpx0 + (WARP_PIX_X - 1), wpy0 + (WARP_PIX_Y - 1));
+            if (hit) {
+                sm.a[lane] = ra;
+                sm.b[lane] = make_float4(rb.x, rb.y, __int_as_float(gid), 0.f);
+                const float4 c = __ldg(rgb + gid);
+                float v[4 * NV];
+                v[0] = c.x; v[1] = c.y; v[2] = c.z;
 #pragma unroll
-                for (int w = 0; w < BLEND_WARPS; ++w)
-                    if ((uint32_t)f >= sm.warp_max[w]) mask &= ~(1u << w);
-                if (mask) {
-                    sm.a[tid] = ra;
-                    sm.b[tid] = rb;
-                    const float4 c = __ldg(rgb + staged_id);
-                    float v[4 * NV];
-                    v[0] = c.x; v[1] = c.y; v[2] = c.z;
+                for (int i = 3; i < 4 * NV; ++i) v[i] = 0.f;
+                if (F > 0) {
+                    const float2* f2 = reinterpret_cast<const float2*>(features + (size_t)gid * GS2M_NUM_FEATURES);
 #pragma unroll
-                    for (int i = 3; i < 4 * NV; ++i) v[i] = 0.f;
-                    if (F > 0) {
-                        const float2* f2 = reinterpret_cast<const float2*>(features + (size_t)staged_id * GS2M_NUM_FEATURES);
-#pragma unroll
-                        for (int i = 0; i < (F + 1) / 2; ++i) {
-                            const float2 t = __ldg(f2 + i);
-                            v[3 + 2 * i] = t.x;
-                            if (2 * i + 1 < F) v[3 + 2 * i + 1] = t.y;
-                        }
+                    for (int i = 0; i < (F + 1) / 2; ++i) {
+                        const float2 t = __ldg(f2 + i);
+                        v[3 + 2 * i] = t.x;
+                        if (2 * i + 1 < F) v[3 + 2 * i + 1] = t.y;
                     }
-#pragma unroll
-                    for (int k = 0; k < NV; ++k)
-                        sm.col[k][tid] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-#pragma unroll
-                    for (int i = 0; i < NG; ++i) sm.acc[tid][i] = 0.f;
                 }
-            }
 #pragma unroll
-            for (int w = 0; w < BLEND_WARPS; ++w) {
-                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
-                if (lane == 0) sm.words[w][warp] = word;
+                for (int k = 0; k < NV; ++k) sm.col[k][lane] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
-            const uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
-            if (lane == 0) sm.touched[warp] = any;
         }
-        __syncthreads();
+        uint32_t word = __ballot_sync(0xffffffffu, hit);
+        __syncwarp();
 
         // ---- evaluate (lane = pixel) / reduce (lane = parked entry) ----
-        for (int sw = 0; sw < BWD_BATCH / 32; ++sw) {
-            uint32_t word = sm.words[warp][sw];
-            while (word != 0) {
-                const int bit = __ffs(word) - 1;
-                word &= word - 1;
-                const int slot = sw * 32 + bit;
-                const uint32_t f = (uint32_t)(n_back - 1 - (batch * BWD_BATCH + slot));
-                float pw = 0.f, pq = 0.f;
-                if (f < my_contrib) {
-                    const float4 ra = sm.a[slot];
-                    const float4 rb = sm.b[slot];
-                    float dx, dy, G, alpha;
-                    if (pair_alpha(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, pxf, pyf, dx, dy, G, alpha)) {
-                        const float one_m_alpha = 1.0f - alpha;
-                        T = __fdiv_rn(T, one_m_alpha);
-                        float c[4 * NV];
+        while (word != 0) {
+            const int slot = __ffs(word) - 1;
+            word &= word - 1;
+            const uint32_t fs = (uint32_t)(n_back - 1 - (base + slot));
+            float pw = 0.f, pq = 0.f;
+            const float4 ra = sm.a[slot];
+            const float4 rb = sm.b[slot];
+            if (fs < my_contrib) {
+                float dx, dy, G, alpha;
+                if (pair_alpha(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, pxf, pyf, dx, dy, G, alpha)) {
+                    const float one_m_alpha = 1.0f - alpha;
+                    T = __fdiv_rn(T, one_m_alpha);
+                    float c[4 * NV];
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) {
-                            const float4 t = sm.col[k][slot];
-                            c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
-                        }
-                        float cd = 0.f;
-#pragma unroll
-                        for (int i = 0; i < NC; ++i) cd = fmaf(c[i], dL[i], cd);
-                        S = fmaf(last_alpha, last_cd - S, S);          // a_prev*cd_prev + (1-a_prev)*S
-                        last_alpha = alpha;
-                        last_cd = cd;
-                        float dL_dalpha = (cd - S) * T;
-                        dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
-                        pw = alpha * T;
-                        pq = dL_dalpha * G;
+                    for (int k = 0; k < NV; ++k) {
+                        const float4 t = sm.col[k][slot];
+                        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
                     }
-                }
-                if (lane == n_parked) my_slot = slot;
-                sm.park_w[warp][n_parked * PARK_STRIDE + lane] = pw;
-                sm.park_q[warp][n_parked * PARK_STRIDE + lane] = pq;
-                ++n_parked;
-                if (n_parked == PARK) {
-                    __syncwarp();
-                    reduce_parked<F>(sm, warp, lane, n_parked, my_slot, wpx0, wpy0, half_w, half_h);
-                    n_parked = 0;
+                    float cd = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) cd = fmaf(c[i], dL[i], cd);
+                    S = fmaf(last_alpha, last_cd - S, S);          // a_prev*cd_prev + (1-a_prev)*S
+                    last_alpha = alpha;
+                    last_cd = cd;
+                    float dL_dalpha = (cd - S) * T;
+                    dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
+                    pw = alpha * T;
+                    pq = dL_dalpha * G;
                 }
             }
+            // an entry no pixel of the block actually blends contributes nothing: do not park it
+            if (!__any_sync(0xffffffffu, (pw != 0.f) || (pq != 0.f))) continue;
+            if (lane == n_parked) { my_ra = ra; my_rb = make_float2(rb.x, rb.y); my_gid = __float_as_int(rb.z); }
+            sm.park_w[n_parked * PARK_STRIDE + lane] = pw;
+            sm.park_q[n_parked * PARK_STRIDE + lane] = pq;
+            ++n_parked;
+            if (n_parked == PARK) {
+                __syncwarp();
+                reduce_parked<F>(sm, lane, n_parked, my_ra, my_rb, my_gid, wpx0, wpy0, half_w, half_h, grad_acc);
+                n_parked = 0;
+            }
         }
-        if (n_parked > 0) {
-            __syncwarp();
-            reduce_parked<F>(sm, warp, lane, n_parked, my_slot, wpx0, wpy0, half_w, half_h);
-            n_parked = 0;
-        }
-        __syncthreads();
-
-        // ---- one set of global atomics per (Gaussian, tile) ----
-        if (tid < BWD_BATCH && mask != 0) {
-            float* dst = grad_acc + (size_t)staged_id * GS2M_ACC_STRIDE;
-#pragma unroll
-            for (int i = 0; i < NG; ++i) atomicAdd(dst + i, sm.acc[tid][i]);
-        }
-        // the next round's staging writes a/b/col/acc of slots whose flush (same thread) is complete; the words are
-        // rewritten by the staging warps only after every consumer passed the barrier above.
+        __syncwarp();   // every lane is done reading this step's staged records
+    }
+    if (n_parked > 0) {
+        __syncwarp();
+        reduce_parked<F>(sm, lane, n_parked, my_ra, my_rb, my_gid, wpx0, wpy0, half_w, half_h, grad_acc);
     }
 }
 
 template <int F>
 int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im, cudaStream_t s) {
     dim3 grid(p.tiles_x, p.tiles_y);
-    const size_t smem = sizeof(BwdSmem<F>);
+    const size_t smem = sizeof(WarpSmemB<F>) * BLEND_WARPS;
     static bool configured = false;
     if (!configured) {
         GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -4,15 +4,15 @@
 // Behavioural reference: renderCUDA (cuda_rasterizer/forward.cu:246-372).  Per pixel the sequence of
 // (power, alpha, test_T, T) values, the termination point, `n_contrib` and the `observe` counts are bit-identical to
 // the reference; what differs is how the work is organised:
-//   * each batch of 256 list entries is staged once into shared memory as 16-byte records (position/conic,
-//     opacity, colour + feature vector) with 128-bit loads, instead of being re-fetched from global per pair;
-//   * while staging, every thread proves for its Gaussian which of the tile's eight 8x4-pixel warp blocks can
-//     possibly receive alpha >= 1/255 (rect_may_contribute); the eight ballots become per-warp bit masks and a
-//     warp only ever evaluates the entries whose bit is set;
-//   * a warp leaves the batch as soon as all of its 32 pixels have terminated; the CTA stops staging when all 256
-//     have (the reference's only exit);
-//   * `observe` increments are aggregated per warp (ballot+popc) into shared counters and flushed once per staged
-//     entry — integer sums, so the totals are exact;
+//   * warp-autonomous walk: each of the CTA's 8 warps owns an 8x4 pixel block and walks the tile list on its own,
+//     32 entries per step, with no block-wide barrier anywhere.  Lane l gathers the 32-byte blend record of entry l
+//     with two 128-bit loads (the 8 warps of a tile read the same records at about the same time -> L1 hits), proves
+//     with the conservative footprint test (rect_may_contribute) whether the entry can give any pixel of the block
+//     alpha >= 1/255, and the ballot of those tests is the warp's work list; survivors also stage their colour +
+//     feature vector as 16-byte shared records, instead of the reference's per-pair global re-fetches;
+//   * a warp stops as soon as all of its 32 pixels have terminated (the reference only leaves when all 256 have);
+//   * `observe` increments are aggregated per warp (ballot + popc): one integer reduction per (entry, warp) — sums of
+//     integers, so the totals are exact;
 //   * F is a template parameter: accumulators stay in registers and the loops unroll.
 #include "blend_common.cuh"
 
@@ -20,13 +20,11 @@ namespace gs2m {
 namespace {
 
 template <int F>
-struct FwdSmem {
+struct WarpSmemF {
     static constexpr int NV = (3 + F + 3) / 4;  // float4s per staged colour+feature vector
-    float4 a[BLEND_THREADS];                    // mean.x, mean.y, conic.a, conic.b
-    float4 b[BLEND_THREADS];                    // conic.c, opacity, -, -
-    float4 col[NV][BLEND_THREADS];              // r,g,b,f0 | f1..f4 | f5..f8 | f9,0,0,0
-    uint32_t words[BLEND_WARPS][BLEND_WARPS];   // [consumer warp][staging warp] -> 32 entry bits
-    int obs[BLEND_THREADS];
+    float4 a[32];                               // mean.x, mean.y, conic.a, conic.b
+    float4 b[32];                               // conic.c, opacity, Gaussian index (bits), -
+    float4 col[NV][32];                         // r,g,b,f0 | f1..f4 | f5..f8 | f9,0,0,0
 };
 
 template <int F>
@@ -36,19 +34,21 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
     float* __restrict__ out_buffer) {
-    __shared__ FwdSmem<F> sm;
-    constexpr int NV = FwdSmem<F>::NV;
+    __shared__ WarpSmemF<F> sm_all[BLEND_WARPS];
+    constexpr int NV = WarpSmemF<F>::NV;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpSmemF<F>& sm = sm_all[warp];
     const int tile_x = blockIdx.x, tile_y = blockIdx.y;
     int px, py;
     pixel_of_thread(tile_x, tile_y, tid, px, py);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
+    const float wpx0 = (float)(tile_x * GS2M_TILE_X + (warp & 1) * WARP_PIX_X);
+    const float wpy0 = (float)(tile_y * GS2M_TILE_Y + (warp >> 1) * WARP_PIX_Y);
 
     const uint2 range = ranges[tile_y * tiles_x + tile_x];
     const int n_list = (int)(range.y - range.x);
-    const int rounds = (n_list + BLEND_THREADS - 1) / BLEND_THREADS;
 
     bool done = !inside;
     float T = 1.0f;
@@ -58,34 +58,27 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(
 #pragma unroll
     for (int i = 0; i < (F > 0 ? F : 1); ++i) Fv[i] = 0.f;
 
-    int staged_id = 0;
-    for (int batch = 0;; ++batch) {
-        const int num_done = __syncthreads_count(done);  // also: every warp has left the previous batch
-        if (batch > 0) {
-            const int c = sm.obs[tid];
-            if (c != 0) atomicAdd(out_observe + staged_id, c);
-        }
-        if (batch == rounds || num_done == BLEND_THREADS) break;
-
-        // ---- stage one batch: 128-bit gathers of the blend records, footprint masks ----
-        const int li = batch * BLEND_THREADS + tid;
-        uint32_t mask = 0;
+    bool warp_done = __all_sync(0xffffffffu, done);
+    for (int base = 0; base < n_list && !warp_done; base += 32) {
+        // ---- lane l examines list entry base+l ----
+        const int li = base + lane;
+        bool hit = false;
         if (li < n_list) {
-            staged_id = (int)point_list[range.x + li];
-            const float4 ra = __ldg(rec_a + staged_id);
-            const float4 rb = __ldg(rec_b + staged_id);
+            const int gid = (int)point_list[range.x + li];
+            const float4 ra = __ldg(rec_a + gid);
+            const float4 rb = __ldg(rec_b + gid);
             const CullRecord cr = make_cull_record(ra, rb);
-            mask = warp_block_mask(cr, tile_x * GS2M_TILE_X, tile_y * GS2M_TILE_Y);
-            if (mask) {
-                sm.a[tid] = ra;
-                sm.b[tid] = rb;
-                const float4 c = __ldg(rgb + staged_id);
+            hit = rect_may_contribute(cr, wpx0, wpy0, wpx0 + (WARP_PIX_X - 1), wpy0 + (WARP_PIX_Y - 1));
+            if (hit) {
+                sm.a[lane] = ra;
+                sm.b[lane] = make_float4(rb.x, rb.y, __int_as_float(gid), 0.f);
+                const float4 c = __ldg(rgb + gid);
                 float v[4 * NV];
                 v[0] = c.x; v[1] = c.y; v[2] = c.z;
 #pragma unroll
                 for (int i = 3; i < 4 * NV; ++i) v[i] = 0.f;
                 if (F > 0) {
-                    const float2* f2 = reinterpret_cast<const float2*>(features + (size_t)staged_id * GS2M_NUM_FEATURES);
+                    const float2* f2 = reinterpret_cast<const float2*>(features + (size_t)gid * GS2M_NUM_FEATURES);
 #pragma unroll
                     for (int i = 0; i < (F + 1) / 2; ++i) {
                         const float2 t = __ldg(f2 + i);
@@ -94,57 +87,47 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NV; ++k) sm.col[k][tid] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                for (int k = 0; k < NV; ++k) sm.col[k][lane] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
         }
-        sm.obs[tid] = 0;
-#pragma unroll
-        for (int w = 0; w < BLEND_WARPS; ++w) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
-            if (lane == 0) sm.words[w][warp] = word;
-        }
-        __syncthreads();
+        uint32_t word = __ballot_sync(0xffffffffu, hit);
+        __syncwarp();
 
-        // ---- blend: each warp walks only the entries whose footprint reaches its 8x4 block ----
-        bool warp_done = __all_sync(0xffffffffu, done);
-        const uint32_t base_contrib = (uint32_t)(batch * BLEND_THREADS) + 1u;
-        for (int sw = 0; sw < BLEND_WARPS && !warp_done; ++sw) {
-            uint32_t word = sm.words[warp][sw];
-            while (word != 0 && !warp_done) {
-                const int bit = __ffs(word) - 1;
-                word &= word - 1;
-                const int slot = sw * 32 + bit;
-                const float4 ra = sm.a[slot];
-                const float4 rb = sm.b[slot];
-                bool obs = false;
-                if (!done) {
-                    float dx, dy, G, alpha;
-                    if (pair_alpha(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, pxf, pyf, dx, dy, G, alpha)) {
-                        const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            float v[4 * NV];
+        // ---- blend the surviving entries in list order ----
+        while (word != 0 && !warp_done) {
+            const int slot = __ffs(word) - 1;
+            word &= word - 1;
+            const float4 ra = sm.a[slot];
+            const float4 rb = sm.b[slot];
+            bool obs = false;
+            if (!done) {
+                float dx, dy, G, alpha;
+                if (pair_alpha(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, pxf, pyf, dx, dy, G, alpha)) {
+                    const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
+                    if (test_T < 0.0001f) {
+                        done = true;
+                    } else {
+                        float v[4 * NV];
 #pragma unroll
-                            for (int k = 0; k < NV; ++k) {
-                                const float4 t = sm.col[k][slot];
-                                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-                            }
-#pragma unroll
-                            for (int ch = 0; ch < 3; ++ch) C[ch] = __fmaf_rn(T, __fmul_rn(alpha, v[ch]), C[ch]);
-#pragma unroll
-                            for (int ch = 0; ch < F; ++ch) Fv[ch] = __fmaf_rn(T, __fmul_rn(alpha, v[3 + ch]), Fv[ch]);
-                            obs = T > 0.5f;
-                            T = test_T;
-                            last_contributor = base_contrib + (uint32_t)slot;
+                        for (int k = 0; k < NV; ++k) {
+                            const float4 t = sm.col[k][slot];
+                            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
                         }
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) C[ch] = __fmaf_rn(T, __fmul_rn(alpha, v[ch]), C[ch]);
+#pragma unroll
+                        for (int ch = 0; ch < F; ++ch) Fv[ch] = __fmaf_rn(T, __fmul_rn(alpha, v[3 + ch]), Fv[ch]);
+                        obs = T > 0.5f;
+                        T = test_T;
+                        last_contributor = (uint32_t)(base + slot) + 1u;
                     }
                 }
-                const uint32_t ob = __ballot_sync(0xffffffffu, obs);
-                if (ob != 0 && lane == 0) atomicAdd(&sm.obs[slot], __popc(ob));
-                warp_done = __all_sync(0xffffffffu, done);
             }
+            const uint32_t ob = __ballot_sync(0xffffffffu, obs);
+            if (ob != 0 && lane == 0) atomicAdd(out_observe + __float_as_int(rb.z), __popc(ob));
+            warp_done = __all_sync(0xffffffffu, done);
         }
+        __syncwarp();   // all lanes are done with this step's staged records
     }
 
     if (inside) {

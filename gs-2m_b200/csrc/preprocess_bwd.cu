@@ -26,12 +26,11 @@ __device__ __forceinline__ float3 operator*(float s, float3 v) { return make_flo
 __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
-template <bool ACC>
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, GeomState g) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+// Per-Gaussian backward math, written once; `io` decides where the results go (straight to global memory, or into
+// the block's shared staging rows that are then copied out with coalesced 128-bit stores).
+template <class IO>
+__device__ __forceinline__ void gaussian_backward(const BwdParams& p, const GeomState& g, const int idx, const bool visible, IO& io) {
     const size_t i = (size_t)idx;
-    const bool visible = p.radii[idx] > 0;
     const int M = p.M;
 
     float acc[GS2M_ACC_STRIDE];
@@ -48,27 +47,19 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
     }
 
     // ---- pass-through gradients ----
-    {
-        float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
-        if (ACC) { float4 t = *o; t.x += acc[0]; t.y += acc[1]; t.z += acc[2]; t.w += acc[3]; *o = t; }
-        else *o = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = make_float4(acc[4], acc[5], 0.f, acc[6]);
-        put<ACC>(p.dL_dopacity + i, acc[7]);
-        put<ACC>(p.dL_dcolor + 3 * i + 0, acc[8]);
-        put<ACC>(p.dL_dcolor + 3 * i + 1, acc[9]);
-        put<ACC>(p.dL_dcolor + 3 * i + 2, acc[10]);
+    io.mean2d(make_float4(acc[0], acc[1], acc[2], acc[3]));
+    io.conic(make_float4(acc[4], acc[5], 0.f, acc[6]));
+    io.opacity(acc[7]);
+    io.color(0, acc[8]); io.color(1, acc[9]); io.color(2, acc[10]);
 #pragma unroll
-        for (int k = 0; k < GS2M_NUM_FEATURES; ++k) put<ACC>(p.dL_dfeatures + GS2M_NUM_FEATURES * i + k, (k < p.F) ? acc[11 + k] : 0.f);
-    }
+    for (int k = 0; k < GS2M_NUM_FEATURES; ++k) io.feature(k, (k < p.F) ? acc[11 + k] : 0.f);
 
     if (!visible) {
-        if (!ACC) {
-            for (int k = 0; k < 3; ++k) p.dL_dmeans3D[3 * i + k] = 0.f;
-            for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * i + k] = 0.f;
-            for (int k = 0; k < 3; ++k) p.dL_dscale[3 * i + k] = 0.f;
-            for (int k = 0; k < 4; ++k) p.dL_drot[4 * i + k] = 0.f;
-            if (p.dL_dsh) for (int k = 0; k < 3 * M; ++k) p.dL_dsh[3 * M * i + k] = 0.f;
-        }
+        for (int k = 0; k < 3; ++k) io.mean3d(k, 0.f);
+        for (int k = 0; k < 6; ++k) io.cov(k, 0.f);
+        for (int k = 0; k < 3; ++k) io.scale(k, 0.f);
+        io.rot(make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int k = 0; k < 3 * M; ++k) io.sh_out(k, 0.f);
         return;
     }
 
@@ -77,63 +68,91 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
     const float3 m = make_float3(p.means3D[3 * i], p.means3D[3 * i + 1], p.means3D[3 * i + 2]);
 
     // =================== conic -> cov2D -> cov3D, mean (via the Jacobian) ===================
+    // This block is numerically ill-conditioned (differences of large products), so the reference's own outputs
+    // move by 1e-5..1e-4 (relative to the tensor max) between runs from atomic-order noise in dL/dconic alone.
+    // To add nothing on top of that, every operation below uses explicit round-to-nearest intrinsics in exactly the
+    // association order of the reference's computeCov2DCUDA as compiled for sm_100 (read from its SASS), so that
+    // identical inputs give bit-identical outputs.
     const float* cov3D = (p.cov3D_precomp ? p.cov3D_precomp : g.cov3D) + 6 * i;
     const float c0 = cov3D[0], c1 = cov3D[1], c2 = cov3D[2], c3 = cov3D[3], c4 = cov3D[4], c5 = cov3D[5];
-    float3 t = make_float3(vm[0] * m.x + vm[4] * m.y + vm[8] * m.z + vm[12],
-                           vm[1] * m.x + vm[5] * m.y + vm[9] * m.z + vm[13],
-                           vm[2] * m.x + vm[6] * m.y + vm[10] * m.z + vm[14]);
-    const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
-    const float txtz = t.x / t.z, tytz = t.y / t.z;
-    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    const float tz_v = __fadd_rn(__fmaf_rn(m.z, vm[10], __fmaf_rn(m.x, vm[2], __fmul_rn(m.y, vm[6]))), vm[14]);
+    const float tx_v = __fadd_rn(__fmaf_rn(m.z, vm[8], __fmaf_rn(m.x, vm[0], __fmul_rn(m.y, vm[4]))), vm[12]);
+    const float ty_v = __fadd_rn(__fmaf_rn(m.z, vm[9], __fmaf_rn(m.x, vm[1], __fmul_rn(m.y, vm[5]))), vm[13]);
+    const float limx = __fmul_rn(p.tan_fovx, 1.3f), limy = __fmul_rn(p.tan_fovy, 1.3f);
+    const float txtz = __fdiv_rn(tx_v, tz_v), tytz = __fdiv_rn(ty_v, tz_v);
+    const float t_x = __fmul_rn(tz_v, fminf(fmaxf(txtz, -limx), limx));
+    const float t_y = __fmul_rn(tz_v, fminf(fmaxf(tytz, -limy), limy));
     const float x_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
     const float y_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
     const float fx = p.focal_x, fy = p.focal_y;
-    const float j00 = fx / t.z, j02 = -(fx * t.x) / (t.z * t.z);
-    const float j11 = fy / t.z, j12 = -(fy * t.y) / (t.z * t.z);
-    // rows of R_w2v
-    const float3 w0 = make_float3(vm[0], vm[4], vm[8]);
-    const float3 w1 = make_float3(vm[1], vm[5], vm[9]);
-    const float3 w2 = make_float3(vm[2], vm[6], vm[10]);
-    const float3 T0 = j00 * w0 + j02 * w2;   // rows of J * R_w2v
-    const float3 T1 = j11 * w1 + j12 * w2;
-    const float3 V0 = make_float3(c0 * T0.x + c1 * T0.y + c2 * T0.z, c1 * T0.x + c3 * T0.y + c4 * T0.z,
-                                  c2 * T0.x + c4 * T0.y + c5 * T0.z);   // Sigma * T0
-    const float3 V1 = make_float3(c0 * T1.x + c1 * T1.y + c2 * T1.z, c1 * T1.x + c3 * T1.y + c4 * T1.z,
-                                  c2 * T1.x + c4 * T1.y + c5 * T1.z);   // Sigma * T1
-    const float a = dot(T0, V0) + 0.3f;      // the backward-only dilation (backward.cu:205-207)
-    const float b = dot(T0, V1);
-    const float c = dot(T1, V1) + 0.3f;
+    const float tzsq = __fmul_rn(tz_v, tz_v);
+    const float j00 = __fdiv_rn(fx, tz_v), j02 = __fdiv_rn(__fmul_rn(t_x, -fx), tzsq);
+    const float j11 = __fdiv_rn(fy, tz_v), j12 = __fdiv_rn(__fmul_rn(t_y, -fy), tzsq);
+    // rows of J * R_w2v
+    const float X0 = __fmaf_rn(vm[2], j02, __fmul_rn(vm[0], j00));
+    const float Y0 = __fmaf_rn(vm[6], j02, __fmul_rn(vm[4], j00));
+    const float Z0 = __fmaf_rn(vm[10], j02, __fmul_rn(vm[8], j00));
+    const float X1 = __fmaf_rn(vm[2], j12, __fmul_rn(vm[1], j11));
+    const float Y1 = __fmaf_rn(vm[6], j12, __fmul_rn(vm[5], j11));
+    const float Z1 = __fmaf_rn(vm[10], j12, __fmul_rn(vm[9], j11));
+    // Sigma * rows
+    const float V00 = __fmaf_rn(c2, Z0, __fmaf_rn(c0, X0, __fmul_rn(c1, Y0)));
+    const float V01 = __fmaf_rn(c4, Z0, __fmaf_rn(c1, X0, __fmul_rn(c3, Y0)));
+    const float V02 = __fmaf_rn(c5, Z0, __fmaf_rn(c2, X0, __fmul_rn(c4, Y0)));
+    const float V10 = __fmaf_rn(c2, Z1, __fmaf_rn(c0, X1, __fmul_rn(c1, Y1)));
+    const float V11 = __fmaf_rn(c4, Z1, __fmaf_rn(c1, X1, __fmul_rn(c3, Y1)));
+    const float V12 = __fmaf_rn(c5, Z1, __fmaf_rn(c2, X1, __fmul_rn(c4, Y1)));
+    // cov2D with the backward-only 0.3 dilation (backward.cu:205-207)
+    const float a = __fadd_rn(__fmaf_rn(Z0, V02, __fmaf_rn(Y0, V01, __fmul_rn(X0, V00))), 0.3f);
+    const float c = __fadd_rn(__fmaf_rn(Z1, V12, __fmaf_rn(Y1, V11, __fmul_rn(X1, V10))), 0.3f);
+    const float b = __fmaf_rn(Z0, V12, __fmaf_rn(Y0, V11, __fmul_rn(X0, V10)));
     const float gx = acc[4], gy = acc[5], gz = acc[6];   // dL/dconic (xx, xy, yy)
-    const float denom = a * c - b * b;
-    const float denom2inv = 1.0f / (denom * denom + 0.0000001f);
+    const float ac = __fmul_rn(a, c);
+    const float denom = __fmaf_rn(-b, b, ac);
+    const float k = __frcp_rn(__fmaf_rn(denom, denom, 0.0000001f));
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (denom2inv != 0.f) {
-        dL_da = denom2inv * (-c * c * gx + 2.f * b * c * gy + (denom - a * c) * gz);
-        dL_dc = denom2inv * (-a * a * gz + 2.f * a * b * gy + (denom - a * c) * gx);
-        dL_db = denom2inv * 2.f * (b * c * gx - (denom + 2.f * b * b) * gy + a * b * gz);
-        dcov[0] = T0.x * T0.x * dL_da + T0.x * T1.x * dL_db + T1.x * T1.x * dL_dc;
-        dcov[3] = T0.y * T0.y * dL_da + T0.y * T1.y * dL_db + T1.y * T1.y * dL_dc;
-        dcov[5] = T0.z * T0.z * dL_da + T0.z * T1.z * dL_db + T1.z * T1.z * dL_dc;
-        dcov[1] = 2.f * T0.x * T0.y * dL_da + (T0.x * T1.y + T0.y * T1.x) * dL_db + 2.f * T1.x * T1.y * dL_dc;
-        dcov[2] = 2.f * T0.x * T0.z * dL_da + (T0.x * T1.z + T0.z * T1.x) * dL_db + 2.f * T1.x * T1.z * dL_dc;
-        dcov[4] = 2.f * T0.z * T0.y * dL_da + (T0.y * T1.z + T0.z * T1.y) * dL_db + 2.f * T1.y * T1.z * dL_dc;
+    if (k != 0.f) {
+        const float b2 = __fadd_rn(b, b);
+        const float d_m_ac = __fadd_rn(-ac, denom);
+        dL_da = __fmul_rn(__fmaf_rn(gz, d_m_ac, __fmaf_rn(gy, __fmul_rn(c, b2), -__fmul_rn(gx, __fmul_rn(c, c)))), k);
+        dL_dc = __fmul_rn(__fmaf_rn(gx, d_m_ac, __fmaf_rn(gy, __fmul_rn(b, __fadd_rn(a, a)), -__fmul_rn(gz, __fmul_rn(a, a)))), k);
+        dL_db = __fmul_rn(__fadd_rn(k, k),
+                          __fmaf_rn(gz, __fmul_rn(b, a), __fmaf_rn(gx, __fmul_rn(b, c), -__fmul_rn(gy, __fmaf_rn(b, b2, denom)))));
+        dcov[0] = __fmaf_rn(dL_dc, __fmul_rn(X1, X1), __fmaf_rn(dL_da, __fmul_rn(X0, X0), __fmul_rn(dL_db, __fmul_rn(X0, X1))));
+        dcov[3] = __fmaf_rn(dL_dc, __fmul_rn(Y1, Y1), __fmaf_rn(dL_da, __fmul_rn(Y0, Y0), __fmul_rn(dL_db, __fmul_rn(Y0, Y1))));
+        dcov[5] = __fmaf_rn(dL_dc, __fmul_rn(Z1, Z1), __fmaf_rn(dL_da, __fmul_rn(Z0, Z0), __fmul_rn(dL_db, __fmul_rn(Z0, Z1))));
+        dcov[1] = __fmaf_rn(dL_dc, __fmul_rn(Y1, __fadd_rn(X1, X1)),
+                            __fmaf_rn(dL_da, __fmul_rn(Y0, __fadd_rn(X0, X0)), __fmul_rn(dL_db, __fmaf_rn(X0, Y1, __fmul_rn(Y0, X1)))));
+        dcov[2] = __fmaf_rn(dL_dc, __fmul_rn(Z1, __fadd_rn(X1, X1)),
+                            __fmaf_rn(dL_da, __fmul_rn(Z0, __fadd_rn(X0, X0)), __fmul_rn(dL_db, __fmaf_rn(X0, Z1, __fmul_rn(Z0, X1)))));
+        dcov[4] = __fmaf_rn(dL_dc, __fmul_rn(Z1, __fadd_rn(Y1, Y1)),
+                            __fmaf_rn(dL_da, __fmul_rn(Y0, __fadd_rn(Z0, Z0)), __fmul_rn(dL_db, __fmaf_rn(Y0, Z1, __fmul_rn(Z0, Y1)))));
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) put<ACC>(p.dL_dcov3D + 6 * i + k, dcov[k]);
+    for (int q = 0; q < 6; ++q) io.cov(q, dcov[q]);
 
     // gradient w.r.t. the rows of J*R, then J, then the view-space mean
-    const float3 dT0 = (2.f * dL_da) * V0 + dL_db * V1;
-    const float3 dT1 = (2.f * dL_dc) * V1 + dL_db * V0;
-    const float dJ00 = dot(w0, dT0), dJ02 = dot(w2, dT0);
-    const float dJ11 = dot(w1, dT1), dJ12 = dot(w2, dT1);
-    const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
-    const float dtx = x_mul * -fx * tz2 * dJ02;
-    const float dty = y_mul * -fy * tz2 * dJ12;
-    const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2.f * fx * t.x) * tz3 * dJ02 + (2.f * fy * t.y) * tz3 * dJ12;
-    float3 dmean = make_float3(vm[0] * dtx + vm[1] * dty + vm[2] * dtz, vm[4] * dtx + vm[5] * dty + vm[6] * dtz,
-                               vm[8] * dtx + vm[9] * dty + vm[10] * dtz);
+    const float dT00 = __fmaf_rn(__fadd_rn(V00, V00), dL_da, __fmul_rn(V10, dL_db));
+    const float dT01 = __fmaf_rn(__fadd_rn(V01, V01), dL_da, __fmul_rn(V11, dL_db));
+    const float dT02 = __fmaf_rn(__fadd_rn(V02, V02), dL_da, __fmul_rn(V12, dL_db));
+    const float dT10 = __fmaf_rn(V00, dL_db, __fmul_rn(__fadd_rn(V10, V10), dL_dc));
+    const float dT11 = __fmaf_rn(V01, dL_db, __fmul_rn(__fadd_rn(V11, V11), dL_dc));
+    const float dT12 = __fmaf_rn(V02, dL_db, __fmul_rn(__fadd_rn(V12, V12), dL_dc));
+    const float dJ00 = __fmaf_rn(vm[8], dT02, __fmaf_rn(vm[0], dT00, __fmul_rn(vm[4], dT01)));
+    const float dJ02 = __fmaf_rn(vm[10], dT02, __fmaf_rn(vm[2], dT00, __fmul_rn(vm[6], dT01)));
+    const float dJ11 = __fmaf_rn(vm[9], dT12, __fmaf_rn(vm[1], dT10, __fmul_rn(vm[5], dT11)));
+    const float dJ12 = __fmaf_rn(vm[10], dT12, __fmaf_rn(vm[2], dT10, __fmul_rn(vm[6], dT11)));
+    const float tz = __frcp_rn(tz_v);
+    const float tz2 = __fmul_rn(tz, tz), tz3 = __fmul_rn(tz2, tz);
+    const float dtx = __fmul_rn(dJ02, __fmul_rn(tz2, __fmul_rn(x_mul, -fx)));
+    const float dty = __fmul_rn(dJ12, __fmul_rn(tz2, __fmul_rn(y_mul, -fy)));
+    float dtz = __fmaf_rn(dJ00, __fmul_rn(tz2, -fx), -__fmul_rn(dJ11, __fmul_rn(tz2, fy)));
+    dtz = __fmaf_rn(dJ02, __fmul_rn(tz3, __fmul_rn(t_x, __fadd_rn(fx, fx))), dtz);
+    dtz = __fmaf_rn(dJ12, __fmul_rn(tz3, __fmul_rn(t_y, __fadd_rn(fy, fy))), dtz);
+    float3 dmean = make_float3(__fmaf_rn(dtz, vm[2], __fmaf_rn(dtx, vm[0], __fmul_rn(dty, vm[1]))),
+                               __fmaf_rn(dtz, vm[6], __fmaf_rn(dtx, vm[4], __fmul_rn(dty, vm[5]))),
+                               __fmaf_rn(dtz, vm[10], __fmaf_rn(dtx, vm[8], __fmul_rn(dty, vm[9]))));
 
     // =================== 2-D mean -> 3-D mean through the projection ===================
     {
@@ -154,8 +173,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
         const float x = d0.x * inv_len, y = d0.y * inv_len, z = d0.z * inv_len;
         const uchar4 cl = reinterpret_cast<const uchar4*>(g.clamped)[idx];
         const float3 dRGB = make_float3(cl.x ? 0.f : acc[8], cl.y ? 0.f : acc[9], cl.z ? 0.f : acc[10]);
-        const float* __restrict__ sh = p.shs + 3 * (size_t)M * i;
-        float* __restrict__ dsh = p.dL_dsh + 3 * (size_t)M * i;
 
         // basis value B[k] and its gradient (Bx,By,Bz) w.r.t. the (unnormalised-treated) direction, per coefficient
         const int D = p.D;
@@ -205,18 +222,19 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
             if (k < M) {
                 const bool active = k < n_active;
                 const float bk = active ? B[k] : 0.f;
-                put<ACC>(dsh + 3 * k + 0, bk * dRGB.x);
-                put<ACC>(dsh + 3 * k + 1, bk * dRGB.y);
-                put<ACC>(dsh + 3 * k + 2, bk * dRGB.z);
+                // read this coefficient before its slot is overwritten with the gradient (the staged sink aliases them)
+                const float s = (active && k > 0) ? io.sh_in(3 * k) * dRGB.x + io.sh_in(3 * k + 1) * dRGB.y + io.sh_in(3 * k + 2) * dRGB.z : 0.f;
+                io.sh_out(3 * k + 0, bk * dRGB.x);
+                io.sh_out(3 * k + 1, bk * dRGB.y);
+                io.sh_out(3 * k + 2, bk * dRGB.z);
                 if (active && k > 0) {
-                    const float s = sh[3 * k] * dRGB.x + sh[3 * k + 1] * dRGB.y + sh[3 * k + 2] * dRGB.z;
                     ddir.x = fmaf(Bx[k], s, ddir.x);
                     ddir.y = fmaf(By[k], s, ddir.y);
                     ddir.z = fmaf(Bz[k], s, ddir.z);
                 }
             }
         }
-        if (!ACC) for (int k = 16; k < M; ++k) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+        for (int k = 48; k < 3 * M; ++k) io.sh_out(k, 0.f);
         // through the normalisation dir = d0/|d0|
         const float s2 = dot(d0, d0);
         const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
@@ -224,9 +242,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
         dmean.y += (-d0.x * d0.y * ddir.x + (s2 - d0.y * d0.y) * ddir.y - d0.z * d0.y * ddir.z) * inv32;
         dmean.z += (-d0.x * d0.z * ddir.x - d0.y * d0.z * ddir.y + (s2 - d0.z * d0.z) * ddir.z) * inv32;
     }
-    put<ACC>(p.dL_dmeans3D + 3 * i + 0, dmean.x);
-    put<ACC>(p.dL_dmeans3D + 3 * i + 1, dmean.y);
-    put<ACC>(p.dL_dmeans3D + 3 * i + 2, dmean.z);
+    io.mean3d(0, dmean.x); io.mean3d(1, dmean.y); io.mean3d(2, dmean.z);
 
     // =================== cov3D -> scale, rotation ===================
     if (p.scales != nullptr) {
@@ -247,26 +263,173 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(BwdParams p, G
         };
         const float3 Gr0 = Gmul(r0), Gr1 = Gmul(r1), Gr2 = Gmul(r2);
         // Sigma = sum_k s_k^2 r_k r_k^T  =>  dL/ds_k = 2 s_k r_k^T G r_k  (w.r.t. the modified scale, as the reference)
-        put<ACC>(p.dL_dscale + 3 * i + 0, 2.f * s0 * dot(r0, Gr0));
-        put<ACC>(p.dL_dscale + 3 * i + 1, 2.f * s1 * dot(r1, Gr1));
-        put<ACC>(p.dL_dscale + 3 * i + 2, 2.f * s2 * dot(r2, Gr2));
+        io.scale(0, 2.f * s0 * dot(r0, Gr0));
+        io.scale(1, 2.f * s1 * dot(r1, Gr1));
+        io.scale(2, 2.f * s2 * dot(r2, Gr2));
         // D_k = dL/dr_k = 2 s_k^2 G r_k ; chain through r_k(q)
         const float3 D0 = (2.f * s0 * s0) * Gr0, D1 = (2.f * s1 * s1) * Gr1, D2 = (2.f * s2 * s2) * Gr2;
         const float dq_r = 2.f * z * (D0.y - D1.x) + 2.f * y * (D2.x - D0.z) + 2.f * x * (D1.z - D2.y);
         const float dq_x = 2.f * y * (D1.x + D0.y) + 2.f * z * (D2.x + D0.z) + 2.f * r * (D1.z - D2.y) - 4.f * x * (D2.z + D1.y);
         const float dq_y = 2.f * x * (D1.x + D0.y) + 2.f * r * (D2.x - D0.z) + 2.f * z * (D1.z + D2.y) - 4.f * y * (D2.z + D0.x);
         const float dq_z = 2.f * r * (D0.y - D1.x) + 2.f * x * (D2.x + D0.z) + 2.f * y * (D1.z + D2.y) - 4.f * z * (D1.y + D0.x);
-        put<ACC>(p.dL_drot + 4 * i + 0, dq_r);
-        put<ACC>(p.dL_drot + 4 * i + 1, dq_x);
-        put<ACC>(p.dL_drot + 4 * i + 2, dq_y);
-        put<ACC>(p.dL_drot + 4 * i + 3, dq_z);
-    } else if (!ACC) {
-        for (int k = 0; k < 3; ++k) p.dL_dscale[3 * i + k] = 0.f;
-        for (int k = 0; k < 4; ++k) p.dL_drot[4 * i + k] = 0.f;
+        io.rot(make_float4(dq_r, dq_x, dq_y, dq_z));
+    } else {
+        for (int k = 0; k < 3; ++k) io.scale(k, 0.f);
+        io.rot(make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    if (p.shs == nullptr && !ACC && p.dL_dsh) {
-        for (int k = 0; k < 3 * M; ++k) p.dL_dsh[3 * M * i + k] = 0.f;
+    if (p.shs == nullptr) {
+        for (int k = 0; k < 3 * M; ++k) io.sh_out(k, 0.f);
     }
+}
+
+
+// ---- sink 1: straight to global memory (any M) ----
+template <bool ACC>
+struct GlobalIO {
+    const BwdParams& p; size_t i;
+    __device__ GlobalIO(const BwdParams& p_, size_t i_) : p(p_), i(i_) {}
+    __device__ void mean2d(float4 v) {
+        float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
+        if (ACC) { float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        *o = v;
+    }
+    __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
+    __device__ void opacity(float v) { put<ACC>(p.dL_dopacity + i, v); }
+    __device__ void color(int k, float v) { put<ACC>(p.dL_dcolor + 3 * i + k, v); }
+    __device__ void feature(int k, float v) { put<ACC>(p.dL_dfeatures + GS2M_NUM_FEATURES * i + k, v); }
+    __device__ void mean3d(int k, float v) { put<ACC>(p.dL_dmeans3D + 3 * i + k, v); }
+    __device__ void cov(int k, float v) { put<ACC>(p.dL_dcov3D + 6 * i + k, v); }
+    __device__ void scale(int k, float v) { put<ACC>(p.dL_dscale + 3 * i + k, v); }
+    __device__ void rot(float4 v) {
+        float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
+        if (ACC) { float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        *o = v;
+    }
+    __device__ float sh_in(int k) const { return __ldg(p.shs + 3 * (size_t)p.M * i + k); }
+    __device__ void sh_out(int k, float v) { if (p.dL_dsh) put<ACC>(p.dL_dsh + 3 * (size_t)p.M * i + k, v); }
+};
+
+// ---- sink 2: rows of a shared staging area (M <= 16); the block copies them out coalesced ----
+constexpr int ST_SH = 48, ST_FEAT = 10, ST_COV = 6, ST_V3 = 3;
+struct StageSmem {
+    float sh[256 * (ST_SH + 1)];    // SH coefficients on the way in, dL/dsh on the way out; row stride (3*M)|1 (odd:
+                                    // conflict-free when every thread walks its own row)
+    float feat[256 * ST_FEAT];
+    float cov[256 * ST_COV];
+    float mean3d[256 * ST_V3];
+    float scale[256 * ST_V3];
+    float color[256 * ST_V3];
+};
+template <bool ACC>
+struct StagedIO {
+    const BwdParams& p; size_t i; StageSmem& sm; int t; int sh_row;
+    __device__ StagedIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
+    __device__ void mean2d(float4 v) {
+        float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
+        if (ACC) { float4 u = *o; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        *o = v;
+    }
+    __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
+    __device__ void opacity(float v) { put<ACC>(p.dL_dopacity + i, v); }
+    __device__ void color(int k, float v) { sm.color[t * ST_V3 + k] = v; }
+    __device__ void feature(int k, float v) { sm.feat[t * ST_FEAT + k] = v; }
+    __device__ void mean3d(int k, float v) { sm.mean3d[t * ST_V3 + k] = v; }
+    __device__ void cov(int k, float v) { sm.cov[t * ST_COV + k] = v; }
+    __device__ void scale(int k, float v) { sm.scale[t * ST_V3 + k] = v; }
+    __device__ void rot(float4 v) {
+        float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
+        if (ACC) { float4 u = *o; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        *o = v;
+    }
+    __device__ float sh_in(int k) const { return sm.sh[t * sh_row + k]; }
+    __device__ void sh_out(int k, float v) { sm.sh[t * sh_row + k] = v; }
+};
+
+// coalesced copy-out of `n` floats of the block's contiguous output region (16-byte aligned start)
+template <bool ACC>
+__device__ __forceinline__ void block_store(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    const int n4 = n >> 2;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int e = threadIdx.x; e < n4; e += 256) {
+        float4 v = s4[e];
+        if (ACC) { const float4 u = d4[e]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        d4[e] = v;
+    }
+    for (int e = (n4 << 2) + threadIdx.x; e < n; e += 256) dst[e] = ACC ? dst[e] + src[e] : src[e];
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdParams p, GeomState g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+    GlobalIO<ACC> io(p, (size_t)idx);
+    gaussian_backward(p, g, idx, p.radii[idx] > 0, io);
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StageSmem& sm = *reinterpret_cast<StageSmem*>(smem_raw);
+    const int t = threadIdx.x;
+    const size_t row0 = (size_t)blockIdx.x * 256;
+    const int rows = (int)min((size_t)256, (size_t)p.P - row0);
+    const int idx = (int)row0 + t;
+    const bool inside = t < rows;
+    const bool visible = inside && p.radii[idx] > 0;
+    const int sh_row = 3 * p.M;
+    // coalesced load of the SH rows of the block's visible Gaussians
+    const int sh_pad = sh_row | 1;
+    if (p.shs != nullptr) {
+        const float* __restrict__ src = p.shs + row0 * sh_row;
+        const int n = rows * sh_row;
+        if ((sh_row & 3) == 0) {      // 128-bit global loads; a float4 never straddles two rows
+            for (int e4 = t; e4 < (n >> 2); e4 += 256) {
+                const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
+                if (p.radii[row0 + r] > 0) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + e4);
+                    float* d = sm.sh + r * sh_pad + c;
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            }
+        } else {
+            for (int e = t; e < n; e += 256) {
+                const int r = e / sh_row, c = e - r * sh_row;
+                if (p.radii[row0 + r] > 0) sm.sh[r * sh_pad + c] = __ldg(src + e);
+            }
+        }
+        __syncthreads();
+    }
+    if (inside) {
+        StagedIO<ACC> io(p, (size_t)idx, sm, t);
+        gaussian_backward(p, g, idx, visible, io);
+    }
+    __syncthreads();
+    if (p.dL_dsh && sh_row > 0) {
+        float* __restrict__ dst = p.dL_dsh + row0 * sh_row;
+        const int n = rows * sh_row;
+        if ((sh_row & 3) == 0) {
+            for (int e4 = t; e4 < (n >> 2); e4 += 256) {
+                const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
+                const float* q = sm.sh + r * sh_pad + c;
+                float4 v = make_float4(q[0], q[1], q[2], q[3]);
+                float4* d4 = reinterpret_cast<float4*>(dst) + e4;
+                if (ACC) { const float4 u = *d4; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+                *d4 = v;
+            }
+        } else {
+            for (int e = t; e < n; e += 256) {
+                const int r = e / sh_row, c = e - r * sh_row;
+                const float v = sm.sh[r * sh_pad + c];
+                dst[e] = ACC ? dst[e] + v : v;
+            }
+        }
+    }
+    block_store<ACC>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT);
+    block_store<ACC>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV);
+    block_store<ACC>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3);
+    block_store<ACC>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3);
+    block_store<ACC>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3);
 }
 
 }  // namespace
@@ -275,8 +438,19 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
     if (p.P == 0) return GS2M_OK;
     const int blocks = (p.P + 255) / 256;
     count_launches(1);
-    if (p.accumulate) preprocess_backward_kernel<true><<<blocks, 256, 0, s>>>(p, g);
-    else preprocess_backward_kernel<false><<<blocks, 256, 0, s>>>(p, g);
+    if (p.M <= 16) {
+        static bool configured = false;
+        if (!configured) {
+            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
+            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
+            configured = true;
+        }
+        if (p.accumulate) preprocess_backward_staged_kernel<true><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
+        else preprocess_backward_staged_kernel<false><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
+    } else {
+        if (p.accumulate) preprocess_backward_generic_kernel<true><<<blocks, 256, 0, s>>>(p, g);
+        else preprocess_backward_generic_kernel<false><<<blocks, 256, 0, s>>>(p, g);
+    }
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }

@@ -122,3 +122,16 @@ def grad_errors(ours, ref):
     denom = ref.double().abs().max().clamp_min(1e-30)
     l2 = d.norm() / ref.double().norm().clamp_min(1e-30)
     return float(d.abs().max() / denom), float(l2)
+
+
+def assert_close_except_flips(actual, expected, rtol, atol, max_flip_frac=2e-3, flip_atol=5e-2):
+    """Rendered planes vs the host-precision oracle: all pixels within (rtol, atol) except a tiny fraction where a
+    borderline alpha >= 1/255 / T < 1e-4 decision is taken differently in host floating point (those move by up to
+    one Gaussian's alpha*colour)."""
+    a, e = actual.double(), expected.double()
+    bad = (a - e).abs() > (atol + rtol * e.abs())
+    frac = bad.double().mean().item()
+    assert frac <= max_flip_frac, "%.5f of the values differ beyond rtol=%g atol=%g" % (frac, rtol, atol)
+    if bad.any():
+        worst = (a - e).abs()[bad].max().item()
+        assert worst <= flip_atol, "largest outlier %.4g exceeds the decision-flip bound %.3g" % (worst, flip_atol)
