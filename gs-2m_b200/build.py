@@ -22,9 +22,13 @@ def _newer(a, b):
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), lib_path=None, obj_subdir="build"):
+    global LIB
+    if lib_path:
+        LIB = lib_path
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    obj_dir = os.path.join(HERE, obj_subdir)
     os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "gs2m_rasterizer.h"))
@@ -34,7 +38,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(obj_dir, s + ".o")
         objs.append(obj)
         if force or _newer(src, obj) or any(_newer(h, obj) for h in headers):
-            jobs.append(["nvcc", "-c"] + NVCC_FLAGS + [src, "-o", obj])
+            jobs.append(["nvcc", "-c"] + NVCC_FLAGS + list(extra_flags) + [src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -55,4 +59,11 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # experiment builds:  python build.py --variant NAME -DFOO=1 ...  ->  lib/variants/NAME.so
+    if "--variant" in sys.argv:
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+        print(build(force=True, extra_flags=flags, lib_path=os.path.join(LIB_DIR, "variants", name + ".so"),
+                    obj_subdir=os.path.join("build", "variant_" + name)))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

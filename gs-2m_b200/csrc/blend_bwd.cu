@@ -31,8 +31,8 @@
 namespace gs2m {
 namespace {
 
-constexpr int PARK = 32;         // entries parked per warp before a reduce
-constexpr int PARK_STRIDE = 33;  // padded row -> conflict-free for both write (lane = pixel) and read (lane = entry)
+constexpr int PARK = 16;         // entries parked per warp before a reduce (2 lanes per entry in the reduce)
+constexpr int PARK_STRIDE = 33;  // padded row -> conflict-free for both write (lane = pixel) and read (lane = entry,half)
 
 template <int F>
 struct WarpSmemB {
@@ -40,7 +40,8 @@ struct WarpSmemB {
     float4 a[32];                  // staged records of the current 32-entry step
     float4 b[32];
     float4 col[NV][32];
-    float4 dpix[32][NV];           // dL/d(colour,features) of the warp's 32 pixels
+    float4 dpix[2][16 * NV + 1];   // dL/d(colour,features) of the warp's 32 pixels, two 16-pixel halves (+16 B skew
+                                   // so that the two halves never share a bank in the reduce)
     float park_w[PARK * PARK_STRIDE];
     float park_q[PARK * PARK_STRIDE];
 };
@@ -49,6 +50,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Reduce phase: lane (e = lane & 15, h = lane >> 4) owns parked entry e and sums over the 16 pixels of half h;
+// the two halves are combined with one shuffle per value and lanes 0..15 issue the vector reductions.
 template <int F>
 __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_parked, float4 ra, float2 rb, int gid,
                                               float wpx0, float wpy0, float half_w, float half_h,
@@ -56,28 +59,38 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
     constexpr int NV = WarpSmemB<F>::NV;
     constexpr int NC = 3 + F;
     constexpr int NG = 11 + F;
-    if (lane < n_parked) {
-        const float gx = ra.x, gy = ra.y, ca = ra.z, cb = ra.w, cc = rb.x, op = rb.y;
+    const int e = lane & 15, h = lane >> 4;
+    // entry data lives in lane e's registers; give lane e+16 a copy
+    ra.x = __shfl_sync(0xffffffffu, ra.x, e); ra.y = __shfl_sync(0xffffffffu, ra.y, e);
+    ra.z = __shfl_sync(0xffffffffu, ra.z, e); ra.w = __shfl_sync(0xffffffffu, ra.w, e);
+    rb.x = __shfl_sync(0xffffffffu, rb.x, e); rb.y = __shfl_sync(0xffffffffu, rb.y, e);
+    const float gx = ra.x, gy = ra.y, ca = ra.z, cb = ra.w, cc = rb.x, op = rb.y;
+    float out[GS2M_ACC_STRIDE];
+#pragma unroll
+    for (int i = 0; i < GS2M_ACC_STRIDE; ++i) out[i] = 0.f;
+    if (e < n_parked) {
         float gc[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) gc[i] = 0.f;
         float sx = 0.f, sy = 0.f, ax = 0.f, ay = 0.f, cxx = 0.f, cxy = 0.f, cyy = 0.f, so = 0.f;
-        const float* pw = &sm.park_w[lane * PARK_STRIDE];
-        const float* pq = &sm.park_q[lane * PARK_STRIDE];
+        const float* pw = &sm.park_w[e * PARK_STRIDE + h * 16];
+        const float* pq = &sm.park_q[e * PARK_STRIDE + h * 16];
+        const float4* dp = sm.dpix[h];
+        const float py_half = wpy0 + (float)(2 * h);
 #pragma unroll 8
-        for (int p = 0; p < 32; ++p) {
-            const float w = pw[p];
-            const float q = pq[p];
+        for (int j = 0; j < 16; ++j) {
+            const float w = pw[j];
+            const float q = pq[j];
             float d[4 * NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                const float4 t = sm.dpix[p][k];
+                const float4 t = dp[j * NV + k];
                 d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
             }
 #pragma unroll
             for (int i = 0; i < NC; ++i) gc[i] = fmaf(w, d[i], gc[i]);
-            const float dx = gx - (wpx0 + (float)(p & 7));
-            const float dy = gy - (wpy0 + (float)(p >> 3));
+            const float dx = gx - (wpx0 + (float)(j & 7));
+            const float dy = gy - (py_half + (float)(j >> 3));
             const float qx = q * fmaf(ca, dx, cb * dy);
             const float qy = q * fmaf(cc, dy, cb * dx);
             sx += qx; sy += qy; ax += fabsf(qx); ay += fabsf(qy);
@@ -87,9 +100,6 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
             cyy = fmaf(qdy, dy, cyy);
             so += q;
         }
-        float out[GS2M_ACC_STRIDE];
-#pragma unroll
-        for (int i = 0; i < GS2M_ACC_STRIDE; ++i) out[i] = 0.f;
         const float kx = op * half_w, ky = op * half_h;
         out[0] = -kx * sx;
         out[1] = -ky * sy;
@@ -101,6 +111,10 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
         out[7] = so;
 #pragma unroll
         for (int i = 0; i < NC; ++i) out[8 + i] = gc[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NG; ++i) out[i] += __shfl_xor_sync(0xffffffffu, out[i], 16);
+    if (h == 0 && e < n_parked) {
         float* dst = grad_acc + (size_t)gid * GS2M_ACC_STRIDE;
 #pragma unroll
         for (int v = 0; v < (NG + 3) / 4; ++v) red_add_v4(dst + 4 * v, out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
@@ -108,8 +122,11 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
     __syncwarp();
 }
 
+#ifndef GS2M_BWD_MINBLOCKS
+#define GS2M_BWD_MINBLOCKS 2
+#endif
 template <int F>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(
+__global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
     const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -147,7 +164,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(
     }
     const float bg_dot = bg[0] * dL[0] + bg[1] * dL[1] + bg[2] * dL[2];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) sm.dpix[lane][k] = make_float4(dL[4 * k], dL[4 * k + 1], dL[4 * k + 2], dL[4 * k + 3]);
+    for (int k = 0; k < NV; ++k)
+        sm.dpix[lane >> 4][(lane & 15) * NV + k] = make_float4(dL[4 * k], dL[4 * k + 1], dL[4 * k + 2], dL[4 * k + 3]);
 
     // deepest contributor of this warp: nothing behind it is ever touched
     uint32_t wmax = my_contrib;
@@ -166,15 +184,23 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_backward_kernel(
     float4 my_ra = make_float4(0.f, 0.f, 0.f, 0.f);
     float2 my_rb = make_float2(0.f, 0.f);
 
+    // software pipeline of the gathers (indices two steps ahead, records one step ahead)
+    const uint32_t* __restrict__ list = point_list + range.x;
+    int gid_cur = (n_back - 1 - lane >= 0) ? (int)list[n_back - 1 - lane] : 0;
+    int gid_nxt = (n_back - 33 - lane >= 0) ? (int)list[n_back - 33 - lane] : 0;
+    float4 ra_cur = make_float4(0.f, 0.f, 0.f, 0.f), rb_cur = ra_cur;
+    if (n_back - 1 - lane >= 0) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
+
     for (int base = 0; base < n_back; base += 32) {
         // ---- lane l looks at entry f = n_back-1-(base+l): back-to-front, lane 0 deepest ----
         const int f = n_back - 1 - (base + lane);
+        const int gid = gid_cur;
+        const float4 ra = ra_cur, rb = rb_cur;
+        gid_cur = gid_nxt;
+        if (f - 32 >= 0) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
+        gid_nxt = (f - 64 >= 0) ? (int)list[f - 64] : 0;
         bool hit = false;
-        int gid = 0;
         if (f >= 0) {
-            gid = (int)point_list[range.x + f];
-            const float4 ra = __ldg(rec_a + gid);
-            const float4 rb = __ldg(rec_b + gid);
             const CullRecord cr = make_cull_record(ra, rb);
             hit = rect_may_contribute(cr, wpx0, wpy0, wpx0 + (WARP_PIX_X - 1), wpy0 + (WARP_PIX_Y - 1));
             if (hit) {

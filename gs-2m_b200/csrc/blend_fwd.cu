@@ -28,7 +28,7 @@ struct WarpSmemF {
 };
 
 template <int F>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(
+__global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
     const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
@@ -59,14 +59,23 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_forward_kernel(
     for (int i = 0; i < (F > 0 ? F : 1); ++i) Fv[i] = 0.f;
 
     bool warp_done = __all_sync(0xffffffffu, done);
+    // software pipeline of the gathers: indices are fetched two steps ahead, records one step ahead, so their
+    // latency is covered by the blending of the current step
+    const uint32_t* __restrict__ list = point_list + range.x;
+    int gid_cur = (lane < n_list) ? (int)list[lane] : 0;
+    int gid_nxt = (32 + lane < n_list) ? (int)list[32 + lane] : 0;
+    float4 ra_cur = make_float4(0.f, 0.f, 0.f, 0.f), rb_cur = ra_cur;
+    if (lane < n_list) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
     for (int base = 0; base < n_list && !warp_done; base += 32) {
         // ---- lane l examines list entry base+l ----
         const int li = base + lane;
+        const int gid = gid_cur;
+        const float4 ra = ra_cur, rb = rb_cur;
+        gid_cur = gid_nxt;
+        if (li + 32 < n_list) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
+        gid_nxt = (li + 64 < n_list) ? (int)list[li + 64] : 0;
         bool hit = false;
         if (li < n_list) {
-            const int gid = (int)point_list[range.x + li];
-            const float4 ra = __ldg(rec_a + gid);
-            const float4 rb = __ldg(rec_b + gid);
             const CullRecord cr = make_cull_record(ra, rb);
             hit = rect_may_contribute(cr, wpx0, wpy0, wpx0 + (WARP_PIX_X - 1), wpy0 + (WARP_PIX_Y - 1));
             if (hit) {

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgs2m_rasterizer.so")
+LIB_PATH = os.environ.get("GS2M_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgs2m_rasterizer.so")
 
 NUM_CHANNELS = 3
 NUM_FEATURES = 10
