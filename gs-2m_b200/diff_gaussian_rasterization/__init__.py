@@ -75,7 +75,12 @@ class _Arena:
     def _resize(self, _user, nbytes):
         try:
             if self.tensor.numel() < nbytes:
-                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                # round large arenas up to 8 MiB so that consecutive views (whose instance count differs a little)
+                # hit the same block of torch's caching allocator instead of triggering cudaMalloc
+                n = int(nbytes)
+                if n > (8 << 20):
+                    n = (n + (8 << 20) - 1) & ~((8 << 20) - 1)
+                self.tensor = torch.empty(n, dtype=torch.uint8, device=self.device)
             return self.tensor.data_ptr()
         except Exception:  # allocation failure -> NULL -> GS2M_ERR_ALLOC
             return None

@@ -32,3 +32,26 @@ for k, (ms, n) in st.items():
     print("%-16s %8.4f ms" % (k, ms / max(n, 1)))
     tot += ms / max(n, 1)
 print("%-16s %8.4f ms" % ("sum", tot))
+
+# ---- host-side view: wall time per fwd+bwd (one sync at the end) and host time spent inside each call ----
+import time
+settings = syn.raster_settings_for(cam, cfg["F"], dgr.GaussianRasterizationSettings)
+lib.gs2m_profile_enable(0)
+torch.cuda.synchronize()
+t_f = t_b = 0.0
+t0 = time.perf_counter()
+for _ in range(iters):
+    a = time.perf_counter()
+    color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities, scene.scales,
+                                                           scene.rotations, None, feats, settings)
+    b = time.perf_counter()
+    dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats, radii, settings, state)
+    c = time.perf_counter()
+    t_f += b - a
+    t_b += c - b
+torch.cuda.synchronize()
+wall = (time.perf_counter() - t0) / iters * 1e3
+print("wall per view %.3f ms | host in forward_raw %.3f ms (includes the R read-back sync) | host in backward_raw %.3f ms"
+      % (wall, t_f / iters * 1e3, t_b / iters * 1e3))
+print("torch allocator: num_alloc_retries", torch.cuda.memory_stats().get("num_alloc_retries"), "cudaMalloc segments",
+      torch.cuda.memory_stats().get("segment.all.allocated"))
