@@ -143,7 +143,13 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         a.prefiltered, a.feature_count = int(bool(rs.prefiltered)), F
         a.out_color, a.out_radii, a.out_observe, a.out_buffer = _ptr(color), _ptr(radii), _ptr(observe), _ptr(buffer)
         a.stream = torch.cuda.current_stream(dev).cuda_stream
-        num_rendered = _native.check(lib.gs2m_rasterize_forward(a), "gs2m_rasterize_forward")
+        try:
+            num_rendered = _native.check(lib.gs2m_rasterize_forward(a), "gs2m_rasterize_forward")
+        finally:
+            # the ctypes callback holds a bound method of its arena: break that reference cycle now so the arenas
+            # (hundreds of MB each) are released by reference counting, not whenever the cyclic GC next runs
+            a.geometry_buffer = a.binning_buffer = a.image_buffer = _native.RESIZE_FN()
+            geom.callback = binning.callback = img.callback = None
     state = RasterState(num_rendered, geom.tensor, binning.tensor, img.tensor)
     return color, radii, observe, buffer, state
 
