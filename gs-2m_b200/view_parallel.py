@@ -23,8 +23,10 @@ import torch
 import torch.distributed as dist
 
 # tensors that are summed over views and ranks: (name, trailing shape as a function of M)
-REDUCED = ("dL_dmeans3D", "dL_dmeans2D", "dL_dsh", "dL_dopacity", "dL_dscale", "dL_drot", "dL_dfeatures",
-           "dL_dcolor", "dL_dcov3D")
+# 73 floats per Gaussian.  dL_dcolor / dL_dcov3D are gradients of the *precomputed* colour / covariance inputs, which GS-2M
+# does not train (it feeds SHs and scale+rotation), so they are per-view scratch here; pass names=REDUCED + (...) to
+# GradientBuckets if a caller does optimise them.
+REDUCED = ("dL_dmeans3D", "dL_dmeans2D", "dL_dsh", "dL_dopacity", "dL_dscale", "dL_drot", "dL_dfeatures")
 
 
 def shard_views(n_views: int, world: int, rank: int) -> range:
