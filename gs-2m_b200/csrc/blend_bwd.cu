@@ -228,16 +228,37 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
         __syncwarp();
 
         // ---- evaluate (lane = pixel) / reduce (lane = parked entry) ----
+        // Two list entries per iteration: their alpha evaluations (the long dependent chain with the expf) are
+        // independent and written branch-free so the scheduler can interleave them; only the T / S recurrences and
+        // the parking are sequential.
         while (word != 0) {
-            const int slot = __ffs(word) - 1;
+            const int slot0 = __ffs(word) - 1;
             word &= word - 1;
-            const uint32_t fs = (uint32_t)(n_back - 1 - (base + slot));
-            float pw = 0.f, pq = 0.f;
-            const float4 ra = sm.a[slot];
-            const float4 rb = sm.b[slot];
-            if (fs < my_contrib) {
-                float dx, dy, G, alpha;
-                if (pair_alpha(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, pxf, pyf, dx, dy, G, alpha)) {
+            const bool two = word != 0;
+            const int slot1 = two ? __ffs(word) - 1 : slot0;
+            if (two) word &= word - 1;
+            const float4 ra0 = sm.a[slot0], rb0 = sm.b[slot0];
+            const float4 ra1 = sm.a[slot1], rb1 = sm.b[slot1];
+            float G0, alpha0, G1, alpha1;
+            bool v0, v1;
+            {
+                float dx, dy;
+                v0 = pair_alpha_nb(ra0.x, ra0.y, ra0.z, ra0.w, rb0.x, rb0.y, pxf, pyf, dx, dy, G0, alpha0);
+                v1 = pair_alpha_nb(ra1.x, ra1.y, ra1.z, ra1.w, rb1.x, rb1.y, pxf, pyf, dx, dy, G1, alpha1);
+            }
+            v0 = v0 && ((uint32_t)(n_back - 1 - (base + slot0)) < my_contrib);
+            v1 = v1 && two && ((uint32_t)(n_back - 1 - (base + slot1)) < my_contrib);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const bool v = u ? v1 : v0;
+                if (u == 1 && !two) break;
+                // an entry no pixel of the block actually blends contributes nothing: skip it entirely
+                if (!__any_sync(0xffffffffu, v)) continue;
+                const int slot = u ? slot1 : slot0;
+                const float alpha = u ? alpha1 : alpha0;
+                const float G = u ? G1 : G0;
+                float pw = 0.f, pq = 0.f;
+                if (v) {
                     const float one_m_alpha = 1.0f - alpha;
                     T = __fdiv_rn(T, one_m_alpha);
                     float c[4 * NV];
@@ -257,17 +278,18 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
                     pw = alpha * T;
                     pq = dL_dalpha * G;
                 }
-            }
-            // an entry no pixel of the block actually blends contributes nothing: do not park it
-            if (!__any_sync(0xffffffffu, (pw != 0.f) || (pq != 0.f))) continue;
-            if (lane == n_parked) { my_ra = ra; my_rb = make_float2(rb.x, rb.y); my_gid = __float_as_int(rb.z); }
-            sm.park_w[n_parked * PARK_STRIDE + lane] = pw;
-            sm.park_q[n_parked * PARK_STRIDE + lane] = pq;
-            ++n_parked;
-            if (n_parked == PARK) {
-                __syncwarp();
-                reduce_parked<F>(sm, lane, n_parked, my_ra, my_rb, my_gid, wpx0, wpy0, half_w, half_h, grad_acc);
-                n_parked = 0;
+                if (lane == n_parked) {
+                    const float4 ra = u ? ra1 : ra0, rb = u ? rb1 : rb0;
+                    my_ra = ra; my_rb = make_float2(rb.x, rb.y); my_gid = __float_as_int(rb.z);
+                }
+                sm.park_w[n_parked * PARK_STRIDE + lane] = pw;
+                sm.park_q[n_parked * PARK_STRIDE + lane] = pq;
+                ++n_parked;
+                if (n_parked == PARK) {
+                    __syncwarp();
+                    reduce_parked<F>(sm, lane, n_parked, my_ra, my_rb, my_gid, wpx0, wpy0, half_w, half_h, grad_acc);
+                    n_parked = 0;
+                }
             }
         }
         __syncwarp();   // every lane is done reading this step's staged records

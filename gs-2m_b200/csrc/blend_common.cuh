@@ -33,6 +33,19 @@ __device__ __forceinline__ bool pair_alpha(float gx, float gy, float ca, float c
     return !(alpha < 0.00392156885936856f);  // 1.0f / 255.0f
 }
 
+// Branch-free variant (same arithmetic, same decisions): lets two independent evaluations be interleaved.
+__device__ __forceinline__ bool pair_alpha_nb(float gx, float gy, float ca, float cb, float cc, float opacity,
+                                              float pxf, float pyf, float& dx, float& dy, float& G, float& alpha) {
+    dx = __fadd_rn(gx, -pxf);
+    dy = __fadd_rn(gy, -pyf);
+    const float s = __fmaf_rn(dx, __fmul_rn(dx, ca), __fmul_rn(dy, __fmul_rn(dy, cc)));
+    const float u = __fmul_rn(dy, __fmul_rn(dx, cb));
+    const float power = __fmaf_rn(s, -0.5f, -u);
+    G = expf(power);
+    alpha = fminf(__fmul_rn(opacity, G), 0.99f);
+    return !(power > 0.0f) & !(alpha < 0.00392156885936856f);
+}
+
 // Lower bound (over an axis-aligned pixel rectangle [x0,x1]x[y0,y1]) of the conic quadratic
 //   q(d) = a dx^2 + 2 b dx dy + c dy^2,   d = pixel - mean,
 // valid when the conic is positive definite.  A pair can only pass the alpha >= 1/255 test where q <= thr
