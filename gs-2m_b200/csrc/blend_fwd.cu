@@ -103,37 +103,53 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
         __syncwarp();
 
         // ---- blend the surviving entries in list order ----
+        // two entries per iteration: both alpha evaluations are independent and branch-free (interleaved by the
+        // scheduler); the blend itself stays strictly in list order
         while (word != 0 && !warp_done) {
-            const int slot = __ffs(word) - 1;
+            const int slot0 = __ffs(word) - 1;
             word &= word - 1;
-            const float4 ra = sm.a[slot];
-            const float4 rb = sm.b[slot];
-            bool obs = false;
-            if (!done) {
-                float dx, dy, G, alpha;
-                if (pair_alpha(ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, pxf, pyf, dx, dy, G, alpha)) {
+            const bool two = word != 0;
+            const int slot1 = two ? __ffs(word) - 1 : slot0;
+            if (two) word &= word - 1;
+            const float4 ra0 = sm.a[slot0], rb0 = sm.b[slot0];
+            const float4 ra1 = sm.a[slot1], rb1 = sm.b[slot1];
+            float G0, alpha0, G1, alpha1;
+            bool v0, v1;
+            {
+                float dx, dy;
+                v0 = pair_alpha_nb(ra0.x, ra0.y, ra0.z, ra0.w, rb0.x, rb0.y, pxf, pyf, dx, dy, G0, alpha0);
+                v1 = pair_alpha_nb(ra1.x, ra1.y, ra1.z, ra1.w, rb1.x, rb1.y, pxf, pyf, dx, dy, G1, alpha1) && two;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                const bool v = u ? v1 : v0;
+                const int slot = u ? slot1 : slot0;
+                const float alpha = u ? alpha1 : alpha0;
+                bool obs = false;
+                if (!done && v) {
                     const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
                     if (test_T < 0.0001f) {
                         done = true;
                     } else {
-                        float v[4 * NV];
+                        float c[4 * NV];
 #pragma unroll
                         for (int k = 0; k < NV; ++k) {
                             const float4 t = sm.col[k][slot];
-                            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+                            c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
                         }
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) C[ch] = __fmaf_rn(T, __fmul_rn(alpha, v[ch]), C[ch]);
+                        for (int ch = 0; ch < 3; ++ch) C[ch] = __fmaf_rn(T, __fmul_rn(alpha, c[ch]), C[ch]);
 #pragma unroll
-                        for (int ch = 0; ch < F; ++ch) Fv[ch] = __fmaf_rn(T, __fmul_rn(alpha, v[3 + ch]), Fv[ch]);
+                        for (int ch = 0; ch < F; ++ch) Fv[ch] = __fmaf_rn(T, __fmul_rn(alpha, c[3 + ch]), Fv[ch]);
                         obs = T > 0.5f;
                         T = test_T;
                         last_contributor = (uint32_t)(base + slot) + 1u;
                     }
                 }
+                const uint32_t ob = __ballot_sync(0xffffffffu, obs);
+                if (ob != 0 && lane == 0) atomicAdd(out_observe + __float_as_int(u ? rb1.z : rb0.z), __popc(ob));
             }
-            const uint32_t ob = __ballot_sync(0xffffffffu, obs);
-            if (ob != 0 && lane == 0) atomicAdd(out_observe + __float_as_int(rb.z), __popc(ob));
             warp_done = __all_sync(0xffffffffu, done);
         }
         __syncwarp();   // all lanes are done with this step's staged records
