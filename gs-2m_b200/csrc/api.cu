@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -64,6 +65,11 @@ size_t GeomState::carve(char* base, int P, GeomState* out) {
     carve_array(p, g.tiles_touched, n);
     carve_array(p, g.point_offsets, n);
     carve_array(p, g.scan_temp, scan_temp_bytes(P));
+    carve_array(p, g.depth_keys, n);
+    carve_array(p, g.depth_keys_alt, n);
+    carve_array(p, g.order_a, n);
+    carve_array(p, g.order_b, n);
+    carve_array(p, g.rank_temp, sort_temp_bytes(P));
     carve_array(p, g.grad_acc, n * GS2M_ACC_STRIDE);
     if (out) *out = g;
     return (size_t)(p - base) + 128;
@@ -90,6 +96,10 @@ size_t ImageState::carve(char* base, int W, int H, ImageState* out) {
     carve_array(p, im.final_T, n);
     carve_array(p, im.n_contrib, n);
     carve_array(p, im.ranges, tiles);
+    carve_array(p, im.tile_counts, 2 * tiles);
+    im.tile_cursor = im.tile_counts + tiles;
+    carve_array(p, im.tile_starts, tiles);
+    carve_array(p, im.bin_info, 4);
     if (out) *out = im;
     return (size_t)(p - base) + 128;
 }
@@ -203,9 +213,16 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     ImageState::carve(img_base, p.W, p.H, &im);
 
     int R = 0;
+    int max_tile_count = 0;
     GeomState g;
     memset(&g, 0, sizeof(g));
     const uint32_t* point_list = nullptr;
+    const uint32_t* rank_order = nullptr;
+    // Binning path: "sort64" (default) = duplicate + 64-bit onesweep radix sort; "ranked" = depth-rank + per-tile
+    // shared-memory sort (binning_v2.cu).  Both give bit-identical lists; on config 4 the 64-bit sort is currently the
+    // faster one on B200 (0.72 ms vs 0.83 ms, profiles/r1_binning_paths.md), so "ranked" is opt-in via GS2M_BINNING.
+    const char* bin_env = getenv("GS2M_BINNING");
+    const bool force_v1 = !(bin_env && strcmp(bin_env, "ranked") == 0);
     if (p.P > 0) {
         char* geom_base = a->geometry_buffer(a->geometry_user, GeomState::carve(nullptr, p.P, nullptr));
         if (!geom_base) { set_error("geometry_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
@@ -215,12 +232,20 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         if (rc != GS2M_OK) return rc;
         { StageTimer t(GS2M_STAGE_SCAN, s); rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s); }
         if (rc != GS2M_OK) return rc;
+        // everything of the binning that does not need the instance buffer runs before the host waits for R
+        if (!force_v1) {
+            StageTimer t(GS2M_STAGE_SORT, s);
+            rc = binning2_rank_and_count(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, s, &rank_order);
+            if (rc != GS2M_OK) return rc;
+        }
         // the instance count sizes the binning arena: one device->host read, like rasterizer_impl.cu:269-270
-        uint32_t r_host = 0;
-        GS2M_CUDA(cudaMemcpyAsync(&r_host, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        uint32_t host_vals[2] = {0, 0};
+        GS2M_CUDA(cudaMemcpyAsync(&host_vals[0], g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (!force_v1) GS2M_CUDA(cudaMemcpyAsync(&host_vals[1], im.bin_info + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         GS2M_CUDA(cudaStreamSynchronize(s));
-        if (r_host >= (1u << 30)) { set_error("%u Gaussian/tile instances exceed the supported 2^30", r_host); return GS2M_ERR_TOO_LARGE; }
-        R = (int)r_host;
+        if (host_vals[0] >= (1u << 30)) { set_error("%u Gaussian/tile instances exceed the supported 2^30", host_vals[0]); return GS2M_ERR_TOO_LARGE; }
+        R = (int)host_vals[0];
+        max_tile_count = (int)host_vals[1];
     }
 
     char* bin_base = a->binning_buffer(a->binning_user, BinState::carve(nullptr, R, nullptr));
@@ -229,7 +254,18 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     BinState::carve(bin_base, R, &b);
     const uint64_t* keys_sorted = b.keys_sorted;
     point_list = b.point_list;
-    if (R > 0) {
+    resolve_sorted(b, n_tiles, keys_sorted, point_list);
+    const bool use_v2 = !force_v1 && p.P > 0 && max_tile_count <= GS2M_TILE_SORT_CAP;
+    if (R > 0 && use_v2) {
+        // the final lists go where the 64-bit sort would have left them (see resolve_sorted); the other key buffer is scratch
+        uint64_t* keys_final = const_cast<uint64_t*>(keys_sorted);
+        uint32_t* vals_final = const_cast<uint32_t*>(point_list);
+        uint64_t* tmp = (keys_final == b.keys_sorted) ? b.keys_unsorted : b.keys_sorted;
+        StageTimer t(GS2M_STAGE_SORT, s);
+        rc = binning2_emit_and_sort(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, rank_order, tmp, keys_final, vals_final,
+                                    max_tile_count, s);
+        if (rc != GS2M_OK) return rc;
+    } else if (R > 0) {
         { StageTimer t(GS2M_STAGE_DUPLICATE, s);
           rc = launch_duplicate_with_keys(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, b.keys_unsorted, b.vals_unsorted, s); }
         if (rc != GS2M_OK) return rc;
@@ -238,11 +274,13 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
           rc = sort_pairs_u64_pingpong(b.keys_unsorted, b.keys_sorted, b.vals_unsorted, b.point_list, R,
                                        32 + tile_bits((uint32_t)n_tiles), b.sort_temp, s, &in_input); }
         if (rc != GS2M_OK) return rc;
-        resolve_sorted(b, n_tiles, keys_sorted, point_list);
         if ((keys_sorted == b.keys_unsorted) != (in_input != 0)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
     }
-    { StageTimer t(GS2M_STAGE_RANGES, s); rc = launch_identify_tile_ranges(R, keys_sorted, im.ranges, n_tiles, s); }
-    if (rc != GS2M_OK) return rc;
+    if (!(use_v2 && p.P > 0)) {   // v2 already wrote the tile ranges from its per-tile counts
+        StageTimer t(GS2M_STAGE_RANGES, s);
+        rc = launch_identify_tile_ranges(R, keys_sorted, im.ranges, n_tiles, s);
+        if (rc != GS2M_OK) return rc;
+    }
     { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
       rc = launch_blend_forward(p, g, point_list, im, a->out_color, a->out_observe, a->out_buffer, s); }
     if (rc != GS2M_OK) return rc;

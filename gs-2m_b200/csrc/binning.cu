@@ -147,14 +147,15 @@ constexpr int RS_MAX_PASSES = 8;
 constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1;
 
 // all digit histograms in one pass over the keys
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const uint64_t* __restrict__ keys, int n, int n_passes,
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __restrict__ keys, int n, int n_passes,
                                                                   int end_bit, uint32_t* __restrict__ hist /*[passes][256]*/) {
     __shared__ uint32_t sh[RS_MAX_PASSES * RS_RADIX];
     for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) sh[i] = 0;
     __syncthreads();
     const int stride = gridDim.x * RS_THREADS;
     for (int i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
+        const KeyT k = keys[i];
         for (int p = 0; p < n_passes; ++p) {
             const int bits = min(8, end_bit - 8 * p);
             const uint32_t d = (uint32_t)(k >> (8 * p)) & ((1u << bits) - 1u);
@@ -178,8 +179,9 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __rest
 
 // One digit pass. Keys are held warp-striped: warp w owns keys [w*32*ITEMS, (w+1)*32*ITEMS) of the tile and lane l
 // holds items l, l+32, ...; stable order inside the tile is therefore (warp, item, lane).
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t* __restrict__ keys_in,
-                                                                 uint64_t* __restrict__ keys_out,
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __restrict__ keys_in,
+                                                                 KeyT* __restrict__ keys_out,
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ vals_out, int n, int shift, int bits,
                                                                  const uint32_t* __restrict__ digit_base /*[256]*/,
@@ -196,12 +198,12 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t*
     const uint32_t mask = (1u << bits) - 1u;
     const int tile_start = (int)tile * RS_TILE + warp * 32 * RS_ITEMS;
 
-    uint64_t key[RS_ITEMS];
+    KeyT key[RS_ITEMS];
     uint32_t rank[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const int g = tile_start + i * 32 + lane;
-        key[i] = (g < n) ? keys_in[g] : ~0ull;
+        key[i] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;
     }
     // rank inside the warp, item by item (stable)
 #pragma unroll
@@ -299,11 +301,12 @@ size_t sort_temp_bytes(int n) {
 
 // Sorts on key bits [0,end_bit). If `result_in_input` is non-null no final copy is made and it reports whether the
 // sorted data ended in the *_in buffers (even number of digit passes) — the forward uses this to avoid a copy.
-int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
-                            int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
+template <typename KeyT>
+static int sort_pairs_pingpong_t(KeyT* keys_in, KeyT* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
+                                 int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
     if (result_in_input) *result_in_input = 0;
     if (n <= 0) return GS2M_OK;
-    if (end_bit <= 0 || end_bit > 64) { set_error("sort_pairs_u64: end_bit %d outside 1..64", end_bit); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (end_bit <= 0 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort_pairs_u64: end_bit %d outside 1..64", end_bit); return GS2M_ERR_INVALID_ARGUMENT; }
     if ((unsigned)n >= RS_VALUE_MASK) { set_error("sort_pairs_u64: %d pairs exceed the 30-bit look-back counters", n); return GS2M_ERR_TOO_LARGE; }
     const int passes = rs_num_passes(end_bit);
     const int tiles = rs_num_tiles(n);
@@ -317,20 +320,20 @@ int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* val
     int hist_blocks = (n + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
     count_launches(2 + passes);
-    rs_histogram_kernel<<<hist_blocks, RS_THREADS, 0, s>>>(keys_in, n, passes, end_bit, hist);
+    rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_in, n, passes, end_bit, hist);
     rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
-    uint64_t* kbuf[2] = {keys_in, keys_out};
+    KeyT* kbuf[2] = {keys_in, keys_out};
     uint32_t* vbuf[2] = {vals_in, vals_out};
     int src = 0;
     if (!(passes & 1) && result_in_input == nullptr) {
         // even number of passes and the caller insists on the *_out buffers: start from a copy in *_out
-        GS2M_CUDA(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        GS2M_CUDA(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * sizeof(KeyT), cudaMemcpyDeviceToDevice, s));
         GS2M_CUDA(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
         src = 1;
     }
     for (int pass = 0; pass < passes; ++pass) {
         const int bits = (end_bit - 8 * pass) < 8 ? (end_bit - 8 * pass) : 8;
-        rs_onesweep_kernel<<<tiles, RS_THREADS, 0, s>>>(kbuf[src], kbuf[src ^ 1], vbuf[src], vbuf[src ^ 1], n, 8 * pass, bits,
+        rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, 0, s>>>(kbuf[src], kbuf[src ^ 1], vbuf[src], vbuf[src ^ 1], n, 8 * pass, bits,
                                                         hist + pass * RS_RADIX, status + (size_t)pass * tiles * RS_RADIX,
                                                         tickets + pass);
         src ^= 1;
@@ -338,6 +341,17 @@ int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* val
     GS2M_CUDA(cudaGetLastError());
     if (result_in_input) *result_in_input = (src == 0);
     return GS2M_OK;
+}
+
+int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
+                            int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
+    return sort_pairs_pingpong_t<uint64_t>(keys_in, keys_out, vals_in, vals_out, n, end_bit, temp, s, result_in_input);
+}
+
+// 32-bit keys (depth ranking of the Gaussians): same kernels, 4 digit passes.
+int sort_pairs_u32_pingpong(uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
+                            int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
+    return sort_pairs_pingpong_t<uint32_t>(keys_in, keys_out, vals_in, vals_out, n, end_bit, temp, s, result_in_input);
 }
 
 int sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit,

@@ -28,6 +28,11 @@ struct GeomState {
     uint32_t* tiles_touched;  // [P]
     uint32_t* point_offsets;  // [P]
     char*     scan_temp;      // gs2m_scan_temp_bytes(P)
+    uint32_t* depth_keys;     // [P] depth bits of visible Gaussians, 0xFFFFFFFF for culled ones (rank sort keys)
+    uint32_t* depth_keys_alt; // [P] ping-pong partner
+    uint32_t* order_a;        // [P] iota on input; rank order (Gaussian index by ascending (depth, index)) after the sort
+    uint32_t* order_b;        // [P] ping-pong partner
+    char*     rank_temp;      // sort_temp_bytes(P)
     float*    grad_acc;       // [P,GS2M_ACC_STRIDE] backward blend accumulator
     static size_t carve(char* base, int P, GeomState* out);
 };
@@ -45,6 +50,10 @@ struct ImageState {
     float*    final_T;        // [N]
     uint32_t* n_contrib;      // [N]
     uint2*    ranges;         // [tiles]
+    uint32_t* tile_counts;    // [tiles] instances per tile            } contiguous: one memset clears both
+    uint32_t* tile_cursor;    // [tiles] emission cursors              }
+    uint32_t* tile_starts;    // [tiles] exclusive scan of the counts
+    uint32_t* bin_info;       // [4] {total instances, longest tile list, -, -}
     static size_t carve(char* base, int W, int H, ImageState* out);
 };
 
@@ -103,6 +112,14 @@ int sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uin
                    char* temp, cudaStream_t s);
 int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
                             int end_bit, char* temp, cudaStream_t s, int* result_in_input);
+int sort_pairs_u32_pingpong(uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
+                            int end_bit, char* temp, cudaStream_t s, int* result_in_input);
+int binning2_rank_and_count(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y, const ImageState& im,
+                            cudaStream_t s, const uint32_t** order_out);
+int binning2_emit_and_sort(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y, const ImageState& im,
+                           const uint32_t* order, uint64_t* tmp, uint64_t* keys_out, uint32_t* vals_out, int max_count,
+                           cudaStream_t s);
+constexpr int GS2M_TILE_SORT_CAP = 8192;   // longest tile list the shared-memory tile sort takes (else: global 64-bit sort)
 size_t scan_temp_bytes(int n);
 int inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, cudaStream_t s);
 

@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
     radii[idx] = 0;
     observe[idx] = 0;
     g.tiles_touched[idx] = 0;
+    g.depth_keys[idx] = 0xFFFFFFFFu;   // culled Gaussians rank behind every visible one
+    g.order_a[idx] = (uint32_t)idx;
 
     const float px = p.means3D[3 * idx + 0], py = p.means3D[3 * idx + 1], pz = p.means3D[3 * idx + 2];
     const float* __restrict__ vm = p.viewmatrix;
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
     const float thr = (opacity >= 0.00392156885936856f) ? 2.0f * logf(255.0f * opacity) : -1.0f;
 
     g.depths[idx] = depth;
+    g.depth_keys[idx] = __float_as_uint(depth);
     radii[idx] = radius;
     g.xy_conic_ab[idx] = make_float4(pix_x, pix_y, conic_x, conic_y);
     g.conic_c_opac[idx] = make_float4(conic_z, opacity, thr, 0.0f);

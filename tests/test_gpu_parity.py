@@ -113,6 +113,22 @@ def test_sh_degrees_and_coefficient_counts(dgr, ref, deg, M):
         assert err <= 5e-4, "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
 
 
+@pytest.mark.parametrize("path", ["ranked", "sort64"])
+def test_both_binning_paths_are_bit_exact(dgr, ref, path, monkeypatch):
+    """GS2M_BINNING selects duplicate + 64-bit onesweep sort (default) or depth-rank + per-tile shared-memory sort;
+    keys, lists and ranges must be bit-identical to the reference with either (includes warp-shared huge rectangles)."""
+    monkeypatch.setenv("GS2M_BINNING", path)
+    for P, W, H, F, scale_big in ((60_000, 640, 400, 10, 1.0), (4_000, 330, 210, 5, 60.0)):
+        scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+        if scale_big != 1.0:
+            sc = scene.scales.clone()
+            sc[:50] *= scale_big
+            scene = scene._replace(scales=sc.contiguous())
+        r = helpers.run_reference(ref, scene, cam, feats, F)
+        o = helpers.run_ours(dgr, scene, cam, feats, F)
+        assert_forward_bit_exact(o, r, P)
+
+
 def test_precomputed_colors_and_covariances(dgr, ref):
     """colors_precomp / cov3D_precomp inputs (binding :186-203; forward.cu:194,227; backward.cu:396,408)."""
     P, W, H, F = 5000, 176, 144, 9
