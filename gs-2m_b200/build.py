@@ -54,7 +54,7 @@ def build(force=False, verbose=False, extra_flags=(), lib_path=None, obj_subdir=
         with open(os.path.join(obj_dir, "ptxas.log"), "w") as f:
             f.write("\n".join(logs))
     if jobs or not os.path.exists(LIB):
-        run(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+        run(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
     return LIB
 
 

@@ -84,16 +84,25 @@ class ViewShardedStep:
     """One data-parallel rasterization step over a batch of views.
 
     ``render_view(view_index, buckets, accumulate) -> dict`` must run forward+backward of one view, adding its
-    gradients into ``buckets.tensors`` (``accumulate`` is False for the first view of the step: the kernels then
-    overwrite, which saves zero-filling the buckets), and may return per-view statistics
+    gradients into ``buckets.tensors`` (``accumulate`` is False for the first view that writes a bucket set: the kernels
+    then overwrite, which saves zero-filling), and may return per-view statistics
     ``{"radii": int32[P], "observe": int32[P]}``.
+
+    With ``n_streams > 1`` (CUDA only) consecutive views of a rank are issued round-robin on that many streams, each with
+    its own bucket set, so the kernels of view k+1 fill the GPU while view k sits in the forward's instance-count
+    read-back or in a tail wave; the bucket sets are summed once per step before the all-reduce.
     """
 
     def __init__(self, P: int, M: int, device, render_view: Callable[[int, GradientBuckets, bool], Optional[dict]],
-                 world: Optional[int] = None, rank: Optional[int] = None):
+                 world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
-        self.buckets = GradientBuckets(P, M, device)
+        self.device = torch.device(device)
+        use_streams = n_streams > 1 and self.device.type == "cuda"
+        self.n_streams = n_streams if use_streams else 1
+        self.bucket_sets = [GradientBuckets(P, M, device) for _ in range(self.n_streams)]
+        self.buckets = self.bucket_sets[0]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)] if use_streams else [None]
         self.render_view = render_view
         self.radii_max = torch.zeros(P, dtype=torch.int32, device=device)
         self.observe_count = torch.zeros(P, dtype=torch.int32, device=device)
@@ -101,20 +110,47 @@ class ViewShardedStep:
     def local_views(self, n_views: int) -> List[int]:
         return list(shard_views(n_views, self.world, self.rank))
 
+    def _one_view(self, v, buckets, accumulate, radii_max, observe_count):
+        stats = self.render_view(v, buckets, accumulate)
+        if stats:
+            if "radii" in stats:
+                torch.maximum(radii_max, stats["radii"], out=radii_max)
+            if "observe" in stats:
+                observe_count += (stats["observe"] > 0).to(torch.int32)
+
     def run(self, n_views: int, reduce: bool = True) -> Dict[str, torch.Tensor]:
         mine = self.local_views(n_views)
         self.radii_max.zero_()
         self.observe_count.zero_()
         if not mine:  # more ranks than views: contribute zeros
             self.buckets.zero_()
-        for k, v in enumerate(mine):
-            stats = self.render_view(v, self.buckets, k > 0)
-            self.buckets.views_accumulated = k + 1
-            if stats:
-                if "radii" in stats:
-                    torch.maximum(self.radii_max, stats["radii"], out=self.radii_max)
-                if "observe" in stats:
-                    self.observe_count += (stats["observe"] > 0).to(torch.int32)
+        if self.n_streams == 1:
+            for k, v in enumerate(mine):
+                self._one_view(v, self.buckets, k > 0, self.radii_max, self.observe_count)
+                self.buckets.views_accumulated = k + 1
+        else:
+            main = torch.cuda.current_stream(self.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            stats = [(torch.zeros_like(self.radii_max), torch.zeros_like(self.observe_count)) for _ in self.streams]
+            used = min(self.n_streams, len(mine))
+            for k, v in enumerate(mine):
+                j = k % self.n_streams
+                with torch.cuda.stream(self.streams[j]):
+                    if k < self.n_streams:
+                        self.streams[j].wait_event(ready)        # inputs / previous step's consumers are done
+                    self._one_view(v, self.bucket_sets[j], k >= self.n_streams, stats[j][0], stats[j][1])
+            for j in range(used):
+                main.wait_stream(self.streams[j])
+            for j in range(used):                                   # fold the per-stream partial sums into set 0
+                torch.maximum(self.radii_max, stats[j][0], out=self.radii_max)
+                self.observe_count += stats[j][1]
+                if j > 0:
+                    for name in self.buckets.names:
+                        self.buckets.tensors[name] += self.bucket_sets[j].tensors[name]
+            for j in range(used):                                   # later work on the side streams must wait for the fold
+                self.streams[j].wait_stream(main)
+            self.buckets.views_accumulated = len(mine)
         if reduce:
             self.buckets.all_reduce()
             reduce_statistics(self.radii_max, self.observe_count)
