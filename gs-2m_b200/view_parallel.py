@@ -43,14 +43,32 @@ def _dist_ready() -> bool:
 
 
 class GradientBuckets:
+    """The per-Gaussian gradient tensors of one rank.  The reduced ones are views into ONE flat fp32 buffer (each view
+    starts on a 128-byte boundary), so the exchange step is a single large all-reduce — at 8 ranks one 0.9 GB
+    collective reaches a much higher bus bandwidth than seven separate ones, three of which are latency-bound."""
+
     def __init__(self, P: int, M: int, device, names: Sequence[str] = REDUCED):
         shapes = {"dL_dmeans3D": (P, 3), "dL_dmeans2D": (P, 4), "dL_dsh": (P, M, 3), "dL_dopacity": (P, 1),
                   "dL_dscale": (P, 3), "dL_drot": (P, 4), "dL_dfeatures": (P, 10), "dL_dcolor": (P, 3),
                   "dL_dcov3D": (P, 6), "dL_dconic": (P, 4)}
         self.names = tuple(names)
-        # dL_dconic is per-view scratch of the backward (never reduced) but the C-ABI wants a pointer for it
-        self.tensors: Dict[str, torch.Tensor] = {n: torch.zeros(shapes[n], dtype=torch.float32, device=device)
-                                                 for n in set(self.names) | set(shapes)}
+
+        def numel(shape):
+            n = 1
+            for d in shape:
+                n *= d
+            return n
+        offsets, total = {}, 0
+        for n in self.names:
+            offsets[n] = total
+            total += (numel(shapes[n]) + 31) // 32 * 32          # 128-byte granularity
+        self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
+        self.tensors: Dict[str, torch.Tensor] = {
+            n: self.flat[offsets[n]:offsets[n] + numel(shapes[n])].view(shapes[n]) for n in self.names}
+        # per-view scratch of the backward (never reduced), but the C-ABI wants a pointer for each
+        for n in shapes:
+            if n not in self.tensors:
+                self.tensors[n] = torch.zeros(shapes[n], dtype=torch.float32, device=device)
         self.views_accumulated = 0
 
     def zero_(self):
@@ -62,12 +80,11 @@ class GradientBuckets:
         return sum(self.tensors[n].numel() * 4 for n in self.names)
 
     def all_reduce(self, async_op: bool = False):
-        """SUM over ranks, one collective per tensor (bucketed per parameter group so that NCCL can start on the
-        first tensor while later ones are still being enqueued). Returns the work handles when ``async_op``."""
+        """SUM over ranks: one collective over the flat buffer. Returns the work handle when ``async_op``."""
         if not _dist_ready():
             return []
-        works = [dist.all_reduce(self.tensors[n], op=dist.ReduceOp.SUM, async_op=async_op) for n in self.names]
-        return works if async_op else []
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return [work] if async_op else []
 
 
 def reduce_statistics(radii_max: torch.Tensor, observe_count: torch.Tensor):
@@ -146,8 +163,7 @@ class ViewShardedStep:
                 torch.maximum(self.radii_max, stats[j][0], out=self.radii_max)
                 self.observe_count += stats[j][1]
                 if j > 0:
-                    for name in self.buckets.names:
-                        self.buckets.tensors[name] += self.bucket_sets[j].tensors[name]
+                    self.buckets.flat += self.bucket_sets[j].flat
             for j in range(used):                                   # later work on the side streams must wait for the fold
                 self.streams[j].wait_stream(main)
             self.buckets.views_accumulated = len(mine)
