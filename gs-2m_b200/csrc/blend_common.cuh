@@ -63,8 +63,8 @@ __device__ __forceinline__ CullRecord make_cull_record(float4 ra, float4 rb) {
     r.mx = ra.x; r.my = ra.y; r.a = ra.z; r.b = ra.w; r.c = rb.x; r.thr = rb.z;
     const float det = r.a * r.c - r.b * r.b;
     r.cullable = (r.a > 0.f) && (r.c > 0.f) && (det > 1e-5f * r.a * r.c);
-    r.inv_a = 1.0f / r.a;
-    r.inv_c = 1.0f / r.c;
+    r.inv_a = __fdividef(1.0f, r.a);   // approximate reciprocals are fine: only the conservative bound uses them and its
+    r.inv_c = __fdividef(1.0f, r.c);   // margin is orders of magnitude above their 2-ulp error
     return r;
 }
 
