@@ -159,10 +159,13 @@ def run_ours(args, cfg, rank, world, device):
 
     # ---- per-kernel device times: same step again with the library's cudaEvent brackets switched on (they sit on the
     # launching stream around every stage; kept out of the region above so that event bookkeeping cannot perturb it)
+    # (single stream: with several views in flight the brackets of one stream would also span the other stream's kernels)
+    step_prof = vp.ViewShardedStep(P, M, device, render_view, world=world, rank=rank, n_streams=1)
+    step_prof.bucket_sets[0] = step_prof.buckets = step.buckets
     lib.gs2m_profile_enable(1)
     _native.profile_read()
     for _ in range(max(1, min(args.steps, 2))):
-        step.run(n_views, reduce=False)
+        step_prof.run(n_views, reduce=False)
     torch.cuda.synchronize(device)
     stage = _native.profile_read()
     lib.gs2m_profile_enable(0)

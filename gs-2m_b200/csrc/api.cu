@@ -83,6 +83,7 @@ size_t BinState::carve(char* base, int R, BinState* out) {
     carve_array(p, b.keys_sorted, n);
     carve_array(p, b.vals_unsorted, n);
     carve_array(p, b.point_list, n);
+    carve_array(p, b.masks, n);
     carve_array(p, b.sort_temp, sort_temp_bytes(R));
     if (out) *out = b;
     return (size_t)(p - base) + 128;
@@ -276,13 +277,19 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         if (rc != GS2M_OK) return rc;
         if ((keys_sorted == b.keys_unsorted) != (in_input != 0)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
     }
-    if (!(use_v2 && p.P > 0)) {   // v2 already wrote the tile ranges from its per-tile counts
+    {
         StageTimer t(GS2M_STAGE_RANGES, s);
-        rc = launch_identify_tile_ranges(R, keys_sorted, im.ranges, n_tiles, s);
+        if (use_v2 && p.P > 0) {   // the ranked path already wrote the tile ranges from its per-tile counts
+            if (R > 0) rc = launch_footprint_masks(p.tiles_x, p.tiles_y, im.ranges, point_list, g, b.masks, s);
+        } else if (p.P > 0) {      // tile ranges + footprint masks in one pass over the sorted list
+            rc = launch_ranges_and_masks(R, p.tiles_x, p.tiles_y, keys_sorted, point_list, g, im.ranges, b.masks, s);
+        } else {
+            rc = launch_identify_tile_ranges(0, keys_sorted, im.ranges, n_tiles, s);
+        }
         if (rc != GS2M_OK) return rc;
     }
     { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
-      rc = launch_blend_forward(p, g, point_list, im, a->out_color, a->out_observe, a->out_buffer, s); }
+      rc = launch_blend_forward(p, g, point_list, b.masks, im, a->out_color, a->out_observe, a->out_buffer, s); }
     if (rc != GS2M_OK) return rc;
     return R;
 }
@@ -335,7 +342,7 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     const uint32_t* point_list;
     resolve_sorted(b, p.tiles_x * p.tiles_y, keys_sorted, point_list);
 
-    { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, im, s); }
+    { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, b.masks, im, s); }
     if (rc != GS2M_OK) return rc;
     { StageTimer t(GS2M_STAGE_PREPROCESS_BWD, s); rc = launch_preprocess_backward(p, g, s); }
     return rc;

@@ -127,8 +127,8 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
 #endif
 template <int F>
 __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backward_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
-    const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
+    int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ grad_color, const float* __restrict__ grad_buffer,
     float* __restrict__ grad_acc) {
@@ -185,24 +185,28 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
     float2 my_rb = make_float2(0.f, 0.f);
 
     // software pipeline of the gathers (indices two steps ahead, records one step ahead)
+    // (the footprint masks written by the forward say which entries reach this warp's block; only those lanes gather)
     const uint32_t* __restrict__ list = point_list + range.x;
+    const uint8_t* __restrict__ mlist = masks + range.x;
     int gid_cur = (n_back - 1 - lane >= 0) ? (int)list[n_back - 1 - lane] : 0;
     int gid_nxt = (n_back - 33 - lane >= 0) ? (int)list[n_back - 33 - lane] : 0;
+    bool hit_cur = (n_back - 1 - lane >= 0) && ((mlist[n_back - 1 - lane] >> warp) & 1);
+    uint32_t m_nxt = (n_back - 33 - lane >= 0) ? mlist[n_back - 33 - lane] : 0u;
     float4 ra_cur = make_float4(0.f, 0.f, 0.f, 0.f), rb_cur = ra_cur;
-    if (n_back - 1 - lane >= 0) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
+    if (hit_cur) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
 
     for (int base = 0; base < n_back; base += 32) {
         // ---- lane l looks at entry f = n_back-1-(base+l): back-to-front, lane 0 deepest ----
         const int f = n_back - 1 - (base + lane);
         const int gid = gid_cur;
+        const bool hit = hit_cur;
         const float4 ra = ra_cur, rb = rb_cur;
         gid_cur = gid_nxt;
-        if (f - 32 >= 0) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
+        hit_cur = (m_nxt >> warp) & 1u;
+        if (hit_cur) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
         gid_nxt = (f - 64 >= 0) ? (int)list[f - 64] : 0;
-        bool hit = false;
-        if (f >= 0) {
-            const CullRecord cr = make_cull_record(ra, rb);
-            hit = rect_may_contribute(cr, wpx0, wpy0, wpx0 + (WARP_PIX_X - 1), wpy0 + (WARP_PIX_Y - 1));
+        m_nxt = (f - 64 >= 0) ? mlist[f - 64] : 0u;
+        {
             if (hit) {
                 sm.a[lane] = ra;
                 sm.b[lane] = make_float4(rb.x, rb.y, __int_as_float(gid), 0.f);
@@ -301,7 +305,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
 }
 
 template <int F>
-int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im, cudaStream_t s) {
+int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
+             cudaStream_t s) {
     dim3 grid(p.tiles_x, p.tiles_y);
     const size_t smem = sizeof(WarpSmemB<F>) * BLEND_WARPS;
     static bool configured = false;
@@ -310,7 +315,7 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
         configured = true;
     }
     count_launches(1);
-    blend_backward_kernel<F><<<grid, BLEND_THREADS, smem, s>>>(im.ranges, point_list, p.W, p.H, p.tiles_x, g.xy_conic_ab,
+    blend_backward_kernel<F><<<grid, BLEND_THREADS, smem, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                                g.conic_c_opac, g.rgb, p.features, p.background,
                                                                im.final_T, im.n_contrib, p.grad_color, p.grad_buffer,
                                                                g.grad_acc);
@@ -320,11 +325,11 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
 
 }  // namespace
 
-int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im,
-                          cudaStream_t s) {
+int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
+                          const ImageState& im, cudaStream_t s) {
     GS2M_CUDA(cudaMemsetAsync(g.grad_acc, 0, (size_t)p.P * GS2M_ACC_STRIDE * sizeof(float), s));
     switch (p.F) {
-#define GS2M_CASE(N) case N: return launch_b<N>(p, g, point_list, im, s);
+#define GS2M_CASE(N) case N: return launch_b<N>(p, g, point_list, masks, im, s);
         GS2M_CASE(0) GS2M_CASE(1) GS2M_CASE(2) GS2M_CASE(3) GS2M_CASE(4) GS2M_CASE(5)
         GS2M_CASE(6) GS2M_CASE(7) GS2M_CASE(8) GS2M_CASE(9) GS2M_CASE(10)
 #undef GS2M_CASE

@@ -94,6 +94,13 @@ __device__ __forceinline__ bool rect_may_contribute(const CullRecord& r, float x
 
 // 8-bit mask: bit w set when warp w's 8x4 pixel block may receive this Gaussian.
 __device__ __forceinline__ uint32_t warp_block_mask(const CullRecord& r, int tile_px0, int tile_py0) {
+    if (r.thr < 0.f) return 0u;
+    if (!r.cullable) return 0xFFu;
+    // the 3-sigma bounding square that put this Gaussian into the tile's list is very conservative: a large share of
+    // the instances cannot reach the tile at all, so test the whole tile first
+    if (!rect_may_contribute(r, (float)tile_px0, (float)tile_py0, (float)(tile_px0 + GS2M_TILE_X - 1),
+                             (float)(tile_py0 + GS2M_TILE_Y - 1)))
+        return 0u;
     uint32_t m = 0;
 #pragma unroll
     for (int w = 0; w < BLEND_WARPS; ++w) {

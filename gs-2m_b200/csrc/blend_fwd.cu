@@ -29,8 +29,8 @@ struct WarpSmemF {
 
 template <int F>
 __global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
-    const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
+    int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
     float* __restrict__ out_buffer) {
@@ -44,8 +44,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
     pixel_of_thread(tile_x, tile_y, tid, px, py);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
-    const float wpx0 = (float)(tile_x * GS2M_TILE_X + (warp & 1) * WARP_PIX_X);
-    const float wpy0 = (float)(tile_y * GS2M_TILE_Y + (warp >> 1) * WARP_PIX_Y);
 
     const uint2 range = ranges[tile_y * tiles_x + tile_x];
     const int n_list = (int)(range.y - range.x);
@@ -61,23 +59,27 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
     bool warp_done = __all_sync(0xffffffffu, done);
     // software pipeline of the gathers: indices are fetched two steps ahead, records one step ahead, so their
     // latency is covered by the blending of the current step
+    // (the footprint masks say which entries reach this warp's block; only those lanes gather a record)
     const uint32_t* __restrict__ list = point_list + range.x;
+    const uint8_t* __restrict__ mlist = masks + range.x;
     int gid_cur = (lane < n_list) ? (int)list[lane] : 0;
     int gid_nxt = (32 + lane < n_list) ? (int)list[32 + lane] : 0;
+    bool hit_cur = (lane < n_list) && ((mlist[lane] >> warp) & 1);
+    uint32_t m_nxt = (32 + lane < n_list) ? mlist[32 + lane] : 0u;
     float4 ra_cur = make_float4(0.f, 0.f, 0.f, 0.f), rb_cur = ra_cur;
-    if (lane < n_list) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
+    if (hit_cur) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
     for (int base = 0; base < n_list && !warp_done; base += 32) {
-        // ---- lane l examines list entry base+l ----
+        // ---- lane l holds list entry base+l ----
         const int li = base + lane;
         const int gid = gid_cur;
+        const bool hit = hit_cur;
         const float4 ra = ra_cur, rb = rb_cur;
         gid_cur = gid_nxt;
-        if (li + 32 < n_list) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
+        hit_cur = (m_nxt >> warp) & 1u;
+        if (hit_cur) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
         gid_nxt = (li + 64 < n_list) ? (int)list[li + 64] : 0;
-        bool hit = false;
-        if (li < n_list) {
-            const CullRecord cr = make_cull_record(ra, rb);
-            hit = rect_may_contribute(cr, wpx0, wpy0, wpx0 + (WARP_PIX_X - 1), wpy0 + (WARP_PIX_Y - 1));
+        m_nxt = (li + 64 < n_list) ? mlist[li + 64] : 0u;
+        {
             if (hit) {
                 sm.a[lane] = ra;
                 sm.b[lane] = make_float4(rb.x, rb.y, __int_as_float(gid), 0.f);
@@ -168,11 +170,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
 }
 
 template <int F>
-int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im, float* out_color,
-             int* out_observe, float* out_buffer, cudaStream_t s) {
+int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
+             float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
     dim3 grid(p.tiles_x, p.tiles_y);
     count_launches(1);
-    blend_forward_kernel<F><<<grid, BLEND_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, p.tiles_x, g.xy_conic_ab,
+    blend_forward_kernel<F><<<grid, BLEND_THREADS, 0, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                            g.conic_c_opac, g.rgb, p.features, p.background, im.final_T,
                                                            im.n_contrib, out_color, out_observe, out_buffer);
     GS2M_CUDA(cudaGetLastError());
@@ -181,10 +183,10 @@ int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list,
 
 }  // namespace
 
-int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im,
-                         float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
+int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
+                         const ImageState& im, float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
     switch (p.F) {
-#define GS2M_CASE(N) case N: return launch_f<N>(p, g, point_list, im, out_color, out_observe, out_buffer, s);
+#define GS2M_CASE(N) case N: return launch_f<N>(p, g, point_list, masks, im, out_color, out_observe, out_buffer, s);
         GS2M_CASE(0) GS2M_CASE(1) GS2M_CASE(2) GS2M_CASE(3) GS2M_CASE(4) GS2M_CASE(5)
         GS2M_CASE(6) GS2M_CASE(7) GS2M_CASE(8) GS2M_CASE(9) GS2M_CASE(10)
 #undef GS2M_CASE

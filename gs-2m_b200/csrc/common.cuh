@@ -42,6 +42,7 @@ struct BinState {
     uint64_t* keys_sorted;    // [R]
     uint32_t* vals_unsorted;  // [R]
     uint32_t* point_list;     // [R]
+    uint8_t*  masks;          // [R] footprint mask of every list entry (bit w: warp block w of the tile may be reached)
     char*     sort_temp;
     static size_t carve(char* base, int R, BinState* out);
 };
@@ -88,8 +89,12 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, ui
 int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y,
                                uint64_t* keys, uint32_t* vals, cudaStream_t s);
 int launch_identify_tile_ranges(int R, const uint64_t* keys_sorted, uint2* ranges, int n_tiles, cudaStream_t s);
-int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im,
-                         float* out_color, int* out_observe, float* out_buffer, cudaStream_t s);
+int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* keys_sorted, const uint32_t* point_list,
+                            const GeomState& g, uint2* ranges, uint8_t* masks, cudaStream_t s);
+int launch_footprint_masks(int tiles_x, int tiles_y, const uint2* ranges, const uint32_t* point_list, const GeomState& g,
+                           uint8_t* masks, cudaStream_t s);
+int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
+                         const ImageState& im, float* out_color, int* out_observe, float* out_buffer, cudaStream_t s);
 
 struct BwdParams {
     int P, D, M, W, H, F, R;
@@ -103,8 +108,8 @@ struct BwdParams {
           *dL_dfeatures;
     int accumulate;
 };
-int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const ImageState& im,
-                          cudaStream_t s);
+int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
+                          const ImageState& im, cudaStream_t s);
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
 
 size_t sort_temp_bytes(int n);

@@ -1,0 +1,71 @@
+// Footprint masks: for every entry of every tile list, which of the tile's eight 8x4-pixel warp blocks can the
+// Gaussian reach with alpha >= 1/255 (conservative test of blend_common.cuh)?  Computed ONCE per (Gaussian, tile)
+// instance after binning and stored as one byte per instance; the forward and the backward blend kernels then read
+// 32 bytes per step instead of each of the 8 warps gathering every record and redoing the test (an ncu source-level
+// profile showed 18 % of the forward's instructions and a third of its stall samples in that per-warp gather + test).
+#include "blend_common.cuh"
+
+namespace gs2m {
+namespace {
+
+__global__ void __launch_bounds__(256) footprint_mask_kernel(int tiles_x, const uint2* __restrict__ ranges,
+                                                             const uint32_t* __restrict__ point_list,
+                                                             const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
+                                                             uint8_t* __restrict__ masks) {
+    const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+    const int px0 = blockIdx.x * GS2M_TILE_X, py0 = blockIdx.y * GS2M_TILE_Y;
+    for (uint32_t i = range.x + threadIdx.x; i < range.y; i += 256) {
+        const uint32_t gid = point_list[i];
+        const CullRecord cr = make_cull_record(__ldg(rec_a + gid), __ldg(rec_b + gid));
+        masks[i] = (uint8_t)warp_block_mask(cr, px0, py0);
+    }
+}
+
+// Same masks, one thread per instance, fused with the tile-range identification of the 64-bit-sort path
+// (identifyTileRanges, rasterizer_impl.cu:108-129): the sorted key gives the tile, the sorted value the Gaussian.
+__global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R, int tiles_x, const uint64_t* __restrict__ keys,
+                                                               const uint32_t* __restrict__ point_list,
+                                                               const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
+                                                               uint2* __restrict__ ranges, uint8_t* __restrict__ masks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t tile = (uint32_t)(keys[i] >> 32);
+    if (i == 0) {
+        ranges[tile].x = 0;
+    } else {
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        if (prev != tile) {
+            ranges[prev].y = (uint32_t)i;
+            ranges[tile].x = (uint32_t)i;
+        }
+    }
+    if (i == R - 1) ranges[tile].y = (uint32_t)R;
+    const uint32_t gid = point_list[i];
+    const CullRecord cr = make_cull_record(__ldg(rec_a + gid), __ldg(rec_b + gid));
+    const int ty = (int)(tile / (uint32_t)tiles_x), tx = (int)(tile - (uint32_t)ty * (uint32_t)tiles_x);
+    masks[i] = (uint8_t)warp_block_mask(cr, tx * GS2M_TILE_X, ty * GS2M_TILE_Y);
+}
+
+}  // namespace
+
+int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* keys_sorted, const uint32_t* point_list,
+                            const GeomState& g, uint2* ranges, uint8_t* masks, cudaStream_t s) {
+    GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
+    if (R > 0) {
+        count_launches(1);
+        ranges_and_masks_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
+                                                                g.conic_c_opac, ranges, masks);
+        GS2M_CUDA(cudaGetLastError());
+    }
+    return GS2M_OK;
+}
+
+int launch_footprint_masks(int tiles_x, int tiles_y, const uint2* ranges, const uint32_t* point_list, const GeomState& g,
+                           uint8_t* masks, cudaStream_t s) {
+    count_launches(1);
+    footprint_mask_kernel<<<dim3(tiles_x, tiles_y), 256, 0, s>>>(tiles_x, ranges, point_list, g.xy_conic_ab, g.conic_c_opac, masks);
+    GS2M_CUDA(cudaGetLastError());
+    return GS2M_OK;
+}
+
+}  // namespace gs2m
