@@ -1,0 +1,73 @@
+"""Fused parameter activation + feature packing (the stage in front of the rasterizer).
+
+``activate_and_pack(xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform, camera_center,
+z_depth=False, blend_metallic=False) -> (scales, rotations, opacities, features)`` replaces, with one CUDA kernel forward
+and one backward, what GS-2M's render facade does with ~15 / ~40 PyTorch kernels per call
+(gaussian_renderer/__init__.py:49-96 over the getters of scene/gaussian_model.py:113-172): the four returned tensors
+are exactly the ``scales=, rotations=, opacities=, features=`` arguments of ``GaussianRasterizer.forward``; gradients
+flow back to the seven RAW parameter tensors.  How render() would use it:
+
+    scales, rotations, opacity, features = activate_and_pack(pc._xyz, pc._scaling, pc._rotation, pc._opacity, pc._albedo,
+        pc._roughness, pc._metallic, viewpoint_camera.world_view_transform, viewpoint_camera.camera_center,
+        z_depth=pipe.z_depth, blend_metallic=blend_metallic)
+"""
+import torch
+
+from . import _native
+
+
+def _f32(t, dev, name):
+    if t.dtype != torch.float32 or t.device != dev:
+        raise RuntimeError("%s must be a float32 tensor on %s" % (name, dev))
+    return t.contiguous()
+
+
+class _ActivateAndPack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, scaling, rotation, opacity, albedo, roughness, metallic, wvt, campos, z_depth, blend_metallic):
+        lib = _native.load()
+        if not xyz.is_cuda:
+            raise RuntimeError("activate_and_pack has no CPU path: inputs must be CUDA tensors")
+        dev = xyz.device
+        P = int(xyz.shape[0])
+        args = [_f32(t, dev, n) for t, n in ((xyz, "xyz"), (scaling, "scaling"), (rotation, "rotation"), (opacity, "opacity"),
+                                             (albedo, "albedo"), (roughness, "roughness"), (metallic, "metallic"),
+                                             (wvt, "world_view_transform"), (campos, "camera_center"))]
+        shapes = ((P, 3), (P, 3), (P, 4), (P, 1), (P, 3), (P, 1), (P, 1), (4, 4), (3,))
+        for t, s in zip(args, shapes):
+            if tuple(t.shape) != s:
+                raise RuntimeError("activate_and_pack: expected shape %s, got %s" % (s, tuple(t.shape)))
+        scales = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        rotations = torch.empty((P, 4), dtype=torch.float32, device=dev)
+        opacities = torch.empty((P, 1), dtype=torch.float32, device=dev)
+        features = torch.empty((P, 10), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_pack_forward(P, *[t.data_ptr() for t in args], int(bool(z_depth)), int(bool(blend_metallic)),
+                                                scales.data_ptr(), rotations.data_ptr(), opacities.data_ptr(),
+                                                features.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                          "gs2m_pack_forward")
+        ctx.save_for_backward(*args)
+        ctx.flags = (int(bool(z_depth)), int(bool(blend_metallic)))
+        return scales, rotations, opacities, features
+
+    @staticmethod
+    def backward(ctx, g_scales, g_rotations, g_opacities, g_features):
+        lib = _native.load()
+        args = ctx.saved_tensors
+        xyz = args[0]
+        dev, P = xyz.device, int(xyz.shape[0])
+        z = lambda shape: torch.zeros(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        ups = [g.contiguous() if g is not None else z(s) for g, s in
+               ((g_scales, (P, 3)), (g_rotations, (P, 4)), (g_opacities, (P, 1)), (g_features, (P, 10)))]
+        outs = [torch.empty(s, dtype=torch.float32, device=dev) for s in ((P, 3), (P, 3), (P, 4), (P, 1), (P, 3), (P, 1), (P, 1))]
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_pack_backward(P, *[t.data_ptr() for t in args], ctx.flags[0], ctx.flags[1],
+                                                 *[t.data_ptr() for t in ups], *[t.data_ptr() for t in outs],
+                                                 torch.cuda.current_stream(dev).cuda_stream), "gs2m_pack_backward")
+        return (*outs, None, None, None, None)
+
+
+def activate_and_pack(xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform, camera_center,
+                      z_depth=False, blend_metallic=False):
+    return _ActivateAndPack.apply(xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform,
+                                  camera_center, z_depth, blend_metallic)

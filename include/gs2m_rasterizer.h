@@ -170,6 +170,25 @@ int gs2m_sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in
 size_t gs2m_scan_temp_bytes(int n);
 int gs2m_inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, void* stream);
 
+/* ---- caller-side stage in front of the rasterizer ----
+ * Fuses what GS-2M does in ~15 (forward) / ~40 (backward) PyTorch kernels per render call: the parameter activations
+ * (scene/gaussian_model.py:113-172: exp, normalize, sigmoid), get_normals (:146-160, utils/general_utils.py:72-92) and the
+ * packing of the 10-column `features` tensor (gaussian_renderer/__init__.py:82-96).  Inputs are the RAW (pre-activation)
+ * parameters [P,3] [P,3] [P,4] [P,1] [P,3] [P,1] [P,1], `world_view_transform` (the 4x4 row-major tensor of W2V^T) and the
+ * camera centre.  Outputs: scales [P,3], rotations [P,4], opacities [P,1], features [P,10].  The backward takes the
+ * rasterizer's gradients w.r.t. those four tensors and returns gradients w.r.t. the raw parameters; `d_xyz` is the extra
+ * term through the distance/depth column, to be added to the rasterizer's dL/dmeans3D. */
+int gs2m_pack_forward(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                      const float* albedo_raw, const float* roughness_raw, const float* metallic_raw,
+                      const float* world_view_transform, const float* campos, int z_depth, int blend_metallic,
+                      float* scales, float* rotations, float* opacities, float* features, void* stream);
+int gs2m_pack_backward(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                       const float* albedo_raw, const float* roughness_raw, const float* metallic_raw,
+                       const float* world_view_transform, const float* campos, int z_depth, int blend_metallic,
+                       const float* dL_dscales, const float* dL_drotations, const float* dL_dopacities, const float* dL_dfeatures,
+                       float* d_xyz, float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw,
+                       float* d_roughness_raw, float* d_metallic_raw, void* stream);
+
 /* ---- per-stage device timing (bench.py's roofline leg) ----
  * When enabled, forward/backward bracket every stage with cudaEvents on the launching stream.  gs2m_profile_read
  * synchronises on the recorded events, ADDS the elapsed milliseconds and launch counts of all completed calls since

@@ -1,0 +1,53 @@
+"""Oracle for the fused activation + feature-packing stage: the SAME PyTorch eager ops GS-2M runs, written out in order,
+differentiable through autograd.  TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+Follows (paths relative to /root/reference):
+  scene/gaussian_model.py:34-44,113-172   activations: exp, torch.nn.functional.normalize, sigmoid
+  scene/gaussian_model.py:146-160         get_normals (argmin one-hot, bmm with build_rotation, in-place flip, normalise)
+  utils/general_utils.py:72-92            build_rotation
+  gaussian_renderer/__init__.py:82-96     cam_normals, cam_points, features columns
+The reference's own modules cannot be imported here (scene/__init__.py pulls plyfile, simple_knn, nvdiffrast — SURVEY.md
+section 8c), so parity for this stage is "unpinned by reference tests": it is anchored on this line-by-line restatement.
+"""
+import torch
+
+
+def build_rotation(r):
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    R = torch.zeros((q.size(0), 3, 3), dtype=r.dtype, device=r.device)
+    r_, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - r_ * z)
+    R[:, 0, 2] = 2 * (x * z + r_ * y)
+    R[:, 1, 0] = 2 * (x * y + r_ * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - r_ * x)
+    R[:, 2, 0] = 2 * (x * z - r_ * y)
+    R[:, 2, 1] = 2 * (y * z + r_ * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def activate_and_pack(xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform, camera_center,
+                      z_depth=False, blend_metallic=False):
+    scales = torch.exp(scaling)
+    rotations = torch.nn.functional.normalize(rotation)
+    opacities = torch.sigmoid(opacity)
+    alb, rough, metal = torch.sigmoid(albedo), torch.sigmoid(roughness), torch.sigmoid(metallic)
+    # get_normals
+    min_idx = torch.argmin(scales, dim=-1, keepdim=True)
+    min_axes = torch.zeros_like(scales).scatter(1, min_idx, 1)
+    R = build_rotation(rotations)
+    normals = torch.bmm(R, min_axes.unsqueeze(-1)).squeeze(-1)
+    view_dirs = camera_center[None] - xyz
+    flip = torch.sum(normals * view_dirs, dim=-1) < 0.0
+    normals = torch.where(flip[:, None], -normals, normals)
+    normals = normals / normals.norm(dim=1, keepdim=True)
+    # render(): features
+    cam_normals = normals @ world_view_transform[:3, :3]
+    cam_points = xyz @ world_view_transform[:3, :3] + world_view_transform[3, :3]
+    cols = [torch.ones_like(xyz[:, :1]),
+            (cam_points[:, 2:3] if z_depth else (cam_normals * cam_points).sum(dim=-1, keepdim=True).abs()),
+            normals, alb, rough, (metal if blend_metallic else torch.zeros_like(metal))]
+    return scales, rotations, opacities, torch.cat(cols, dim=1)

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Fused activation + feature packing vs the PyTorch-eager ops GS-2M runs (oracle/pack_reference.py on the GPU):
+forward+backward time at P = 3 M, CUDA events."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for sub in ("gs-2m_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, sub))
+import pack_reference as ref  # noqa: E402
+import synthetic_scenes as syn  # noqa: E402
+from diff_gaussian_rasterization.packing import activate_and_pack  # noqa: E402
+from test_feature_pack import _raw_params  # noqa: E402
+
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 3_000_000
+cam = syn.camera_to(syn.make_cameras(1, 1959, 1090, radius=2.2)[0], "cuda")
+raw = {k: v.cuda().requires_grad_(True) for k, v in _raw_params(P).items()}
+ups = None
+
+
+def run(fn):
+    global ups
+    out = fn(*raw.values(), cam.world_view_transform, cam.camera_center, blend_metallic=True)
+    if ups is None:
+        ups = [torch.randn_like(t) for t in out]
+    torch.autograd.backward(list(out), ups)
+    for v in raw.values():
+        v.grad = None
+
+
+for name, fn in (("torch eager (reference ops)", ref.activate_and_pack), ("fused CUDA", activate_and_pack)):
+    for _ in range(3):
+        run(fn)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(fn); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-30s P=%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, P, min(ts), sorted(ts)[len(ts) // 2]))
