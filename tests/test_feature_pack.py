@@ -51,6 +51,9 @@ def test_cuda_pack_matches_oracle(z_depth, blend_metallic):
     torch.autograd.backward(list(out), [u.float().cuda() for u in ups])
     for k in raw:
         a, b = raw[k].grad.cpu().double(), raw64[k].grad
+        if b is None:            # no path in the eager graph (e.g. metallic when it is not blended): we return zeros
+            assert float(a.abs().max()) == 0.0, k
+            continue
         err = (a - b).abs().max() / b.abs().max().clamp_min(1e-30)
         assert err <= 2e-5, "%s: %.3e" % (k, err)
 
