@@ -92,21 +92,55 @@ __device__ __forceinline__ bool rect_may_contribute(const CullRecord& r, float x
     return !(qmin > r.thr + 1e-5f * mag + 1e-3f);
 }
 
-// 8-bit mask: bit w set when warp w's 8x4 pixel block may receive this Gaussian.
+// 8-bit mask: bit w set when warp w's 8x4 pixel block may receive this Gaussian.  Same test as rect_may_contribute for
+// the eight blocks of a tile, with everything that only depends on the block's column (2 of them) or row (4) hoisted.
 __device__ __forceinline__ uint32_t warp_block_mask(const CullRecord& r, int tile_px0, int tile_py0) {
     if (r.thr < 0.f) return 0u;
     if (!r.cullable) return 0xFFu;
-    // the 3-sigma bounding square that put this Gaussian into the tile's list is very conservative: a large share of
-    // the instances cannot reach the tile at all, so test the whole tile first
-    if (!rect_may_contribute(r, (float)tile_px0, (float)tile_py0, (float)(tile_px0 + GS2M_TILE_X - 1),
-                             (float)(tile_py0 + GS2M_TILE_Y - 1)))
-        return 0u;
+    const float b2 = 2.f * r.b, ab = fabsf(b2);
+    // per column c (x range [lx,hx]) / per row w (y range [ly,hy])
+    float lx[2], hx[2], ex[2], qx0[2], qx1[2], tx[2], mx2[2], mxb[2];
+    bool inx[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        lx[c] = (float)(tile_px0 + c * WARP_PIX_X) - r.mx;
+        hx[c] = lx[c] + (float)(WARP_PIX_X - 1);
+        inx[c] = (lx[c] <= 0.f) && (hx[c] >= 0.f);
+        ex[c] = (lx[c] > 0.f) ? lx[c] : hx[c];          // nearest vertical edge (used when !inx)
+        qx0[c] = r.a * ex[c] * ex[c];                   // q on that edge = qx0 + (qx1 + c*dy)*dy
+        qx1[c] = b2 * ex[c];
+        tx[c] = -r.b * ex[c] * r.inv_c;                 // unconstrained minimiser in dy
+        const float ax = fmaxf(fabsf(lx[c]), fabsf(hx[c]));
+        mx2[c] = r.a * ax * ax;
+        mxb[c] = ab * ax;
+    }
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < BLEND_WARPS; ++w) {
-        const float x0 = (float)(tile_px0 + (w & 1) * WARP_PIX_X);
-        const float y0 = (float)(tile_py0 + (w >> 1) * WARP_PIX_Y);
-        if (rect_may_contribute(r, x0, y0, x0 + (WARP_PIX_X - 1), y0 + (WARP_PIX_Y - 1))) m |= 1u << w;
+    for (int w = 0; w < 4; ++w) {
+        const float ly = (float)(tile_py0 + w * WARP_PIX_Y) - r.my, hy = ly + (float)(WARP_PIX_Y - 1);
+        const bool iny = (ly <= 0.f) && (hy >= 0.f);
+        const float ey = (ly > 0.f) ? ly : hy;
+        const float qy0 = r.c * ey * ey, qy1 = b2 * ey, ty = -r.b * ey * r.inv_a;
+        const float ay = fmaxf(fabsf(ly), fabsf(hy));
+        const float my2 = r.c * ay * ay;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            bool may = inx[c] && iny;
+            if (!may) {
+                float qmin = 3.0e38f;
+                if (!inx[c]) {
+                    const float dy = fminf(fmaxf(tx[c], ly), hy);
+                    qmin = qx0[c] + (qx1[c] + r.c * dy) * dy;
+                }
+                if (!iny) {
+                    const float dx = fminf(fmaxf(ty, lx[c]), hx[c]);
+                    qmin = fminf(qmin, qy0 + (qy1 + r.a * dx) * dx);
+                }
+                const float mag = mx2[c] + my2 + mxb[c] * ay;
+                may = !(qmin > r.thr + 1e-5f * mag + 1e-3f);
+            }
+            if (may) m |= 1u << (2 * w + c);
+        }
     }
     return m;
 }
