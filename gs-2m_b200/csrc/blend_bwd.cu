@@ -263,8 +263,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
                 const float G = u ? G1 : G0;
                 float pw = 0.f, pq = 0.f;
                 if (v) {
-                    const float one_m_alpha = 1.0f - alpha;
-                    T = __fdiv_rn(T, one_m_alpha);
+                    // one correctly-rounded reciprocal serves both T / (1 - alpha) and T_final / (1 - alpha)
+                    // (backward.cu:532,572 divide twice; the <= 1 ulp difference per step is far inside the 1e-4 gate)
+                    const float inv_one_m_alpha = __frcp_rn(1.0f - alpha);
+                    T *= inv_one_m_alpha;
                     float c[4 * NV];
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
                     last_alpha = alpha;
                     last_cd = cd;
                     float dL_dalpha = (cd - S) * T;
-                    dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
+                    dL_dalpha = fmaf(-T_final * inv_one_m_alpha, bg_dot, dL_dalpha);
                     pw = alpha * T;
                     pq = dL_dalpha * G;
                 }
