@@ -13,9 +13,10 @@ the repo) with plain ``nvcc``/``g++`` commands — not the reference's
 ``setup.py``/CMake — for ``compute_100/sm_100`` with exactly the flag set torch's
 ``CUDAExtension`` would use (no fast-math), and links
 them into ``oracle/_ref/diff_gaussian_rasterization/_C*.so``.  The reference's
-15-line Python binding (``diff_gaussian_rasterization/__init__.py``) is placed
-beside it at build time so the module imports under its own name.  ``oracle/_ref``
-is git-ignored (build output) but travels to the GPU box with the snapshot.
+Python binding (``diff_gaussian_rasterization/__init__.py``) is byte-compiled
+(``py_compile``) to ``__init__.pyc`` beside it — a build artefact, no reference
+source is copied — so the unmodified binding imports under its own package.
+``oracle/_ref`` is git-ignored (build output) but travels to the GPU box.
 
 Usage:  python oracle/build_ref.py [--force]
 """
@@ -46,7 +47,7 @@ def so_path():
 
 
 def available():
-    return os.path.exists(so_path()) and os.path.exists(os.path.join(PKG, "__init__.py"))
+    return os.path.exists(so_path()) and os.path.exists(os.path.join(PKG, "__init__.pyc"))
 
 
 def _run(cmd):
@@ -103,8 +104,13 @@ def build(force=False, verbose=True):
             "-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart",
             f"-Wl,-rpath,{torch_lib}"])
     _run(link)
-    # the reference's Python binding file is placed next to the built module (build output, git-ignored)
-    shutil.copyfile(os.path.join(REF, "diff_gaussian_rasterization/__init__.py"), os.path.join(PKG, "__init__.py"))
+    # the reference's Python binding, byte-compiled next to the built module (build output, git-ignored)
+    import py_compile
+    py_compile.compile(os.path.join(REF, "diff_gaussian_rasterization/__init__.py"), cfile=os.path.join(PKG, "__init__.pyc"),
+                       doraise=True)
+    stale = os.path.join(PKG, "__init__.py")
+    if os.path.exists(stale):
+        os.remove(stale)
     shutil.rmtree(OBJ, ignore_errors=True)
     return so_path()
 
@@ -118,8 +124,10 @@ def load():
     name = "_gs2m_reference_dgr"
     if name in sys.modules:
         return sys.modules[name]
+    import importlib.machinery
     import torch  # noqa: F401
-    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG, "__init__.py"),
+    pyc = os.path.join(PKG, "__init__.pyc")
+    spec = importlib.util.spec_from_file_location(name, pyc, loader=importlib.machinery.SourcelessFileLoader(name, pyc),
                                                   submodule_search_locations=[PKG])
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
