@@ -46,6 +46,9 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
         for (int k = 0; k < GS2M_ACC_STRIDE; ++k) acc[k] = 0.f;
     }
 
+    // a culled Gaussian contributes exactly zero: in accumulate mode (+=) there is nothing to do for it at all
+    if (!visible && IO::kAccumulate) return;
+
     // ---- pass-through gradients ----
     io.mean2d(make_float4(acc[0], acc[1], acc[2], acc[3]));
     io.conic(make_float4(acc[4], acc[5], 0.f, acc[6]));
@@ -286,6 +289,7 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 // ---- sink 1: straight to global memory (any M) ----
 template <bool ACC>
 struct GlobalIO {
+    static constexpr bool kAccumulate = ACC;
     const BwdParams& p; size_t i;
     __device__ GlobalIO(const BwdParams& p_, size_t i_) : p(p_), i(i_) {}
     __device__ void mean2d(float4 v) {
@@ -319,9 +323,11 @@ struct StageSmem {
     float mean3d[256 * ST_V3];
     float scale[256 * ST_V3];
     float color[256 * ST_V3];
+    unsigned char vis[256];         // row visibility: accumulate mode skips the rows of culled Gaussians
 };
 template <bool ACC>
 struct StagedIO {
+    static constexpr bool kAccumulate = ACC;
     const BwdParams& p; size_t i; StageSmem& sm; int t; int sh_row;
     __device__ StagedIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
     __device__ void mean2d(float4 v) {
@@ -346,17 +352,29 @@ struct StagedIO {
 };
 
 // coalesced copy-out of `n` floats of the block's contiguous output region (16-byte aligned start)
-template <bool ACC>
-__device__ __forceinline__ void block_store(float* __restrict__ dst, const float* __restrict__ src, int n) {
+template <bool ACC, int ROW>
+__device__ __forceinline__ void block_store(float* __restrict__ dst, const float* __restrict__ src, int n,
+                                            const unsigned char* __restrict__ vis) {
     const int n4 = n >> 2;
     float4* d4 = reinterpret_cast<float4*>(dst);
     const float4* s4 = reinterpret_cast<const float4*>(src);
     for (int e = threadIdx.x; e < n4; e += 256) {
+        if (ACC && !(vis[(4 * e) / ROW] | vis[(4 * e + 3) / ROW])) continue;   // += 0 for culled rows: skip the RMW
         float4 v = s4[e];
-        if (ACC) { const float4 u = d4[e]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        if (ACC) {
+            // rows of culled Gaussians hold no staged values in accumulate mode: mask them out element-wise
+            const float4 u = d4[e];
+            v.x = vis[(4 * e) / ROW] ? v.x + u.x : u.x;
+            v.y = vis[(4 * e + 1) / ROW] ? v.y + u.y : u.y;
+            v.z = vis[(4 * e + 2) / ROW] ? v.z + u.z : u.z;
+            v.w = vis[(4 * e + 3) / ROW] ? v.w + u.w : u.w;
+        }
         d4[e] = v;
     }
-    for (int e = (n4 << 2) + threadIdx.x; e < n; e += 256) dst[e] = ACC ? dst[e] + src[e] : src[e];
+    for (int e = (n4 << 2) + threadIdx.x; e < n; e += 256) {
+        if (ACC) { if (vis[e / ROW]) dst[e] += src[e]; }
+        else dst[e] = src[e];
+    }
 }
 
 template <bool ACC>
@@ -400,6 +418,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         }
         __syncthreads();
     }
+    sm.vis[t] = visible ? 1 : 0;
     if (inside) {
         StagedIO<ACC> io(p, (size_t)idx, sm, t);
         gaussian_backward(p, g, idx, visible, io);
@@ -411,6 +430,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         if ((sh_row & 3) == 0) {
             for (int e4 = t; e4 < (n >> 2); e4 += 256) {
                 const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
+                if (ACC && !sm.vis[r]) continue;
                 const float* q = sm.sh + r * sh_pad + c;
                 float4 v = make_float4(q[0], q[1], q[2], q[3]);
                 float4* d4 = reinterpret_cast<float4*>(dst) + e4;
@@ -420,16 +440,17 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         } else {
             for (int e = t; e < n; e += 256) {
                 const int r = e / sh_row, c = e - r * sh_row;
+                if (ACC && !sm.vis[r]) continue;
                 const float v = sm.sh[r * sh_pad + c];
                 dst[e] = ACC ? dst[e] + v : v;
             }
         }
     }
-    block_store<ACC>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT);
-    block_store<ACC>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV);
-    block_store<ACC>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3);
-    block_store<ACC>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3);
-    block_store<ACC>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3);
+    block_store<ACC, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
+    block_store<ACC, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
+    block_store<ACC, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
+    block_store<ACC, ST_V3>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
+    block_store<ACC, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
 }
 
 }  // namespace

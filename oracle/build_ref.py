@@ -14,7 +14,7 @@ the repo) with plain ``nvcc``/``g++`` commands — not the reference's
 ``CUDAExtension`` would use (no fast-math), and links
 them into ``oracle/_ref/diff_gaussian_rasterization/_C*.so``.  The reference's
 Python binding (``diff_gaussian_rasterization/__init__.py``) is byte-compiled
-(``py_compile``) to ``__init__.pyc`` beside it — a build artefact, no reference
+(``py_compile``) to ``binding_bytecode.bin`` beside it — a build artefact, no reference
 source is copied — so the unmodified binding imports under its own package.
 ``oracle/_ref`` is git-ignored (build output) but travels to the GPU box.
 
@@ -40,6 +40,7 @@ CU_SOURCES = [
     "rasterize_points.cu",
 ]
 CPP_SOURCES = ["ext.cpp"]
+BINDING = "binding_bytecode.bin"   # byte-compiled reference __init__.py (not named *.pyc: those are not shipped to the GPU box)
 
 
 def so_path():
@@ -47,7 +48,7 @@ def so_path():
 
 
 def available():
-    return os.path.exists(so_path()) and os.path.exists(os.path.join(PKG, "__init__.pyc"))
+    return os.path.exists(so_path()) and os.path.exists(os.path.join(PKG, BINDING))
 
 
 def _run(cmd):
@@ -106,7 +107,7 @@ def build(force=False, verbose=True):
     _run(link)
     # the reference's Python binding, byte-compiled next to the built module (build output, git-ignored)
     import py_compile
-    py_compile.compile(os.path.join(REF, "diff_gaussian_rasterization/__init__.py"), cfile=os.path.join(PKG, "__init__.pyc"),
+    py_compile.compile(os.path.join(REF, "diff_gaussian_rasterization/__init__.py"), cfile=os.path.join(PKG, BINDING),
                        doraise=True)
     stale = os.path.join(PKG, "__init__.py")
     if os.path.exists(stale):
@@ -126,7 +127,7 @@ def load():
         return sys.modules[name]
     import importlib.machinery
     import torch  # noqa: F401
-    pyc = os.path.join(PKG, "__init__.pyc")
+    pyc = os.path.join(PKG, BINDING)
     spec = importlib.util.spec_from_file_location(name, pyc, loader=importlib.machinery.SourcelessFileLoader(name, pyc),
                                                   submodule_search_locations=[PKG])
     mod = importlib.util.module_from_spec(spec)
