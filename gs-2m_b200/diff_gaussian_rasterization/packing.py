@@ -71,3 +71,49 @@ def activate_and_pack(xyz, scaling, rotation, opacity, albedo, roughness, metall
                       z_depth=False, blend_metallic=False):
     return _ActivateAndPack.apply(xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform,
                                   camera_center, z_depth, blend_metallic)
+
+
+class _DeriveMaps(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, buffer, wvt, fx, fy, cx, cy, z_depth):
+        lib = _native.load()
+        if not buffer.is_cuda:
+            raise RuntimeError("derive_maps has no CPU path: buffer must be a CUDA tensor")
+        dev = buffer.device
+        buffer = _f32(buffer, dev, "buffer")
+        wvt = _f32(wvt, dev, "world_view_transform")
+        if buffer.dim() != 3 or buffer.shape[0] != 10:
+            raise RuntimeError("buffer must be (10, H, W)")
+        H, W = int(buffer.shape[1]), int(buffer.shape[2])
+        local_normal = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        mask = torch.empty((1, H, W), dtype=torch.bool, device=dev)
+        ctx.geom = (W, H, float(fx), float(fy), float(cx), float(cy), int(bool(z_depth)))
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_postblend_forward(*ctx.geom, wvt.data_ptr(), buffer.data_ptr(), local_normal.data_ptr(),
+                                                     depth.data_ptr(), mask.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "gs2m_postblend_forward")
+        ctx.save_for_backward(buffer, wvt)
+        ctx.mark_non_differentiable(mask)
+        return local_normal, depth, mask
+
+    @staticmethod
+    def backward(ctx, g_local_normal, g_depth, _g_mask):
+        lib = _native.load()
+        buffer, wvt = ctx.saved_tensors
+        dev = buffer.device
+        W, H = ctx.geom[0], ctx.geom[1]
+        gl = g_local_normal.contiguous() if g_local_normal is not None else torch.zeros((3, H, W), device=dev)
+        gd = g_depth.contiguous() if g_depth is not None else torch.zeros((1, H, W), device=dev)
+        g_buffer = torch.empty((10, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_postblend_backward(*ctx.geom, wvt.data_ptr(), buffer.data_ptr(), gl.data_ptr(), gd.data_ptr(),
+                                                      g_buffer.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                          "gs2m_postblend_backward")
+        return g_buffer, None, None, None, None, None, None
+
+
+def derive_maps(buffer, world_view_transform, fx, fy, cx, cy, z_depth=False):
+    """(local_normal_map[3,H,W], depth_map[1,H,W], normal_mask[1,H,W] bool) from the rasterizer's buffer — the fused form of
+    gaussian_renderer/__init__.py:125-141 (with scene/cameras.py:71-81 rays); differentiable w.r.t. ``buffer``."""
+    return _DeriveMaps.apply(buffer, world_view_transform, fx, fy, cx, cy, z_depth)

@@ -189,6 +189,18 @@ int gs2m_pack_backward(int P, const float* xyz, const float* scaling_raw, const 
                        float* d_xyz, float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw,
                        float* d_roughness_raw, float* d_metallic_raw, void* stream);
 
+/* ---- caller-side stage behind the rasterizer ----
+ * Per-pixel maps GS-2M derives from the blended buffer with ~10 PyTorch kernels (gaussian_renderer/__init__.py:125-141,
+ * scene/cameras.py:71-81): local_normal_map[3,H,W] = buffer[2:5] rotated into camera space, normal_mask[H,W] (all three
+ * normal channels non-zero), depth_map[1,H,W] = distance / -(local_normal . ray + 1e-8) with ray = ((x-cx)/fx, (y-cy)/fy, 1)
+ * (or buffer[1] itself when z_depth).  The backward returns dL/dbuffer [10,H,W] (zero on the channels without a path). */
+int gs2m_postblend_forward(int width, int height, float fx, float fy, float cx, float cy, int z_depth,
+                           const float* world_view_transform, const float* buffer, float* local_normal_map, float* depth_map,
+                           uint8_t* normal_mask, void* stream);
+int gs2m_postblend_backward(int width, int height, float fx, float fy, float cx, float cy, int z_depth,
+                            const float* world_view_transform, const float* buffer, const float* dL_dlocal_normal_map,
+                            const float* dL_ddepth_map, float* dL_dbuffer, void* stream);
+
 /* ---- per-stage device timing (bench.py's roofline leg) ----
  * When enabled, forward/backward bracket every stage with cudaEvents on the launching stream.  gs2m_profile_read
  * synchronises on the recorded events, ADDS the elapsed milliseconds and launch counts of all completed calls since

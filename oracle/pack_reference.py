@@ -51,3 +51,21 @@ def activate_and_pack(xyz, scaling, rotation, opacity, albedo, roughness, metall
             (cam_points[:, 2:3] if z_depth else (cam_normals * cam_points).sum(dim=-1, keepdim=True).abs()),
             normals, alb, rough, (metal if blend_metallic else torch.zeros_like(metal))]
     return scales, rotations, opacities, torch.cat(cols, dim=1)
+
+
+def derive_maps(buffer, world_view_transform, fx, fy, cx, cy, z_depth=False):
+    """gaussian_renderer/__init__.py:125-141 with the rays of scene/cameras.py:71-81 (scale = 1), eager ops in order."""
+    H, W = buffer.shape[1], buffer.shape[2]
+    normal_map = buffer[2:5, ...]
+    normal_mask = (normal_map != 0).all(0, keepdim=True).detach()
+    local_normals = normal_map.permute(1, 2, 0).reshape(-1, 3)
+    local_normals = local_normals @ world_view_transform[:3, :3]
+    local_normal_map = local_normals.reshape(H, W, 3).permute(2, 0, 1)
+    depth_map = buffer[1:2, ...]
+    if not z_depth:
+        u, v = torch.meshgrid(torch.arange(W, dtype=buffer.dtype, device=buffer.device),
+                              torch.arange(H, dtype=buffer.dtype, device=buffer.device), indexing="xy")
+        rays = torch.stack(((u - cx) / fx, (v - cy) / fy, torch.ones_like(u)), dim=-1).view(-1, 3)
+        denoms = torch.sum(local_normals * rays, dim=-1).view(1, H, W)
+        depth_map = buffer[1:2, ...] / -(denoms + 1e-8)
+    return local_normal_map, depth_map, normal_mask

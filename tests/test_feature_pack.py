@@ -74,3 +74,34 @@ def test_packed_features_drive_the_rasterizer_like_the_python_packer():
     b = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, feats, st)
     torch.testing.assert_close(a[0], b[0], rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(a[3], b[3], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("z_depth", [False, True])
+def test_cuda_derive_maps_matches_oracle(z_depth):
+    """Fused post-blend map derivation vs the eager ops, forward and backward."""
+    from diff_gaussian_rasterization.packing import derive_maps
+    H, W = 213, 331
+    g = torch.Generator().manual_seed(5)
+    buf64 = torch.randn(10, H, W, generator=g, dtype=torch.float64)
+    buf64[2:5, :40, :50] = 0.0                     # background pixels: mask false
+    buf64[1] = buf64[1].abs() + 0.5
+    buf64.requires_grad_(True)
+    cam = syn.make_cameras(1, W, H)[0]
+    fx, fy, cx, cy = 1.1 * W, 1.1 * W, 0.5 * W, 0.5 * H
+    ref_out = ref.derive_maps(buf64, cam.world_view_transform.double(), fx, fy, cx, cy, z_depth=z_depth)
+    buf = buf64.detach().float().cuda().requires_grad_(True)
+    out = derive_maps(buf, cam.world_view_transform.cuda(), fx, fy, cx, cy, z_depth=z_depth)
+    torch.testing.assert_close(out[0].cpu().double(), ref_out[0], rtol=1e-5, atol=1e-6)
+    # plane depth divides by (n . ray): where that is ~0 the value (and its gradient) is ill-conditioned; compare where it is not
+    denom = (buf64[1:2] / ref_out[1]).detach().abs() if not z_depth else torch.ones_like(ref_out[1])
+    ok = denom > 0.05
+    torch.testing.assert_close(out[1].cpu().double()[ok], ref_out[1][ok], rtol=1e-4, atol=1e-5)
+    assert torch.equal(out[2].cpu(), ref_out[2])
+    ups = [torch.randn(3, H, W, generator=g, dtype=torch.float64), torch.randn(1, H, W, generator=g, dtype=torch.float64) * 1e-2]
+    torch.autograd.backward([ref_out[0], ref_out[1]], ups)
+    torch.autograd.backward([out[0], out[1]], [u.float().cuda() for u in ups])
+    a, b = buf.grad.cpu().double(), buf64.grad
+    ok = ok.expand_as(b)
+    err = ((a - b).abs() / (b.abs() + 1e-2 * b.abs().mean()))[ok].max()
+    assert err <= 1e-3, "relative error %.3e" % err

@@ -40,3 +40,29 @@ for name, fn in (("torch eager (reference ops)", ref.activate_and_pack), ("fused
         e0.record(); run(fn); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print("%-30s P=%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, P, min(ts), sorted(ts)[len(ts) // 2]))
+
+
+# ---- post-blend map derivation at the headline resolution ----
+from diff_gaussian_rasterization.packing import derive_maps  # noqa: E402
+
+H, W = 1090, 1959
+buf = torch.randn(10, H, W, device="cuda").requires_grad_(True)
+gl, gd = torch.randn(3, H, W, device="cuda"), torch.randn(1, H, W, device="cuda")
+
+
+def run_maps(fn):
+    ln, d, _ = fn(buf, cam.world_view_transform, 1.1 * W, 1.1 * W, 0.5 * W, 0.5 * H)
+    torch.autograd.backward([ln, d], [gl, gd])
+    buf.grad = None
+
+
+for name, fn in (("torch eager (reference ops)", ref.derive_maps), ("fused CUDA", derive_maps)):
+    for _ in range(3):
+        run_maps(fn)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run_maps(fn); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-30s derive_maps %dx%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, W, H, min(ts), sorted(ts)[len(ts) // 2]))
