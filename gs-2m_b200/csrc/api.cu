@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -64,7 +65,7 @@ size_t GeomState::carve(char* base, int P, GeomState* out) {
     carve_array(p, g.clamped, n * 4);
     carve_array(p, g.tiles_touched, n);
     carve_array(p, g.point_offsets, n);
-    carve_array(p, g.scan_temp, scan_temp_bytes(P));
+    carve_array(p, g.scan_temp, std::max(scan_temp_bytes(P), compact_temp_bytes(P)));
     carve_array(p, g.depth_keys, n);
     carve_array(p, g.depth_keys_alt, n);
     carve_array(p, g.order_a, n);
@@ -112,11 +113,16 @@ static int tile_bits(uint32_t n_tiles) {
     return b;
 }
 
-// The sorted lists end in the "unsorted" buffers when the digit-pass count is even (no final copy is made).
-static void resolve_sorted(const BinState& b, int n_tiles, const uint64_t*& keys, const uint32_t*& vals) {
-    const int passes = (32 + tile_bits((uint32_t)n_tiles) + 7) / 8;
-    if (passes & 1) { keys = b.keys_sorted; vals = b.point_list; }
-    else            { keys = b.keys_unsorted; vals = b.vals_unsorted; }
+// Every binning path leaves the sorted lists in BinState::keys_sorted / point_list: the ping-pong sorts are started in
+// whichever buffer makes their last digit pass land there (no final copy).
+static int digit_passes(int key_bits) { return (key_bits + 7) / 8; }
+
+enum BinningPath { BIN_DEPTHFIRST = 0, BIN_SORT64 = 1, BIN_RANKED = 2 };
+static BinningPath binning_path_from_env() {
+    const char* e = getenv("GS2M_BINNING");
+    if (e && strcmp(e, "sort64") == 0) return BIN_SORT64;
+    if (e && strcmp(e, "ranked") == 0) return BIN_RANKED;
+    return BIN_DEPTHFIRST;
 }
 
 static int validate_common(int P, int D, int M, int W, int H, int F, const void* means3D, const void* shs,
@@ -213,17 +219,17 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     ImageState im;
     ImageState::carve(img_base, p.W, p.H, &im);
 
-    int R = 0;
+    int R = 0, V = 0;
     int max_tile_count = 0;
     GeomState g;
     memset(&g, 0, sizeof(g));
-    const uint32_t* point_list = nullptr;
     const uint32_t* rank_order = nullptr;
-    // Binning path: "sort64" (default) = duplicate + 64-bit onesweep radix sort; "ranked" = depth-rank + per-tile
-    // shared-memory sort (binning_v2.cu).  Both give bit-identical lists; on config 4 the 64-bit sort is currently the
-    // faster one on B200 (0.72 ms vs 0.83 ms, profiles/r1_binning_paths.md), so "ranked" is opt-in via GS2M_BINNING.
-    const char* bin_env = getenv("GS2M_BINNING");
-    const bool force_v1 = !(bin_env && strcmp(bin_env, "ranked") == 0);
+    // Binning path (all three give bit-identical keys / lists / ranges, tests/test_gpu_parity.py):
+    //   "depthfirst" (default)  depth-sort the visible Gaussians, emit in depth order, 2-pass sort on the tile id
+    //   "sort64"                duplicate + 64-bit onesweep radix sort, the reference's structure
+    //   "ranked"                depth-rank + atomic per-tile emission + shared-memory tile sort (binning_v2.cu)
+    // B200, config 4: 0.42 / 0.72 / 0.83 ms (profiles/r1_binning_paths.md); GS2M_BINNING selects the other two.
+    BinningPath path = binning_path_from_env();
     if (p.P > 0) {
         char* geom_base = a->geometry_buffer(a->geometry_user, GeomState::carve(nullptr, p.P, nullptr));
         if (!geom_base) { set_error("geometry_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
@@ -231,61 +237,88 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
 
         { StageTimer t(GS2M_STAGE_PREPROCESS_FWD, s); rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, s); }
         if (rc != GS2M_OK) return rc;
-        { StageTimer t(GS2M_STAGE_SCAN, s); rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s); }
-        if (rc != GS2M_OK) return rc;
-        // everything of the binning that does not need the instance buffer runs before the host waits for R
-        if (!force_v1) {
-            StageTimer t(GS2M_STAGE_SORT, s);
-            rc = binning2_rank_and_count(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, s, &rank_order);
+        uint32_t host_vals[2] = {0, 0};
+        if (path == BIN_DEPTHFIRST) {
+            // point_offsets + compaction of the visible Gaussians to (depth bits, index) in one scan; {R, V} -> bin_info[2..3]
+            { StageTimer t(GS2M_STAGE_SCAN, s); rc = binning_df_compact(p.P, g, g.depth_keys_alt, g.order_b, im.bin_info + 2, s); }
             if (rc != GS2M_OK) return rc;
+            GS2M_CUDA(cudaMemcpyAsync(host_vals, im.bin_info + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        } else {
+            { StageTimer t(GS2M_STAGE_SCAN, s); rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s); }
+            if (rc != GS2M_OK) return rc;
+            // everything of the binning that does not need the instance buffer runs before the host waits for R
+            if (path == BIN_RANKED) {
+                StageTimer t(GS2M_STAGE_SORT, s);
+                rc = binning2_rank_and_count(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, s, &rank_order);
+                if (rc != GS2M_OK) return rc;
+            }
+            GS2M_CUDA(cudaMemcpyAsync(&host_vals[0], g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (path == BIN_RANKED) GS2M_CUDA(cudaMemcpyAsync(&host_vals[1], im.bin_info + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         }
         // the instance count sizes the binning arena: one device->host read, like rasterizer_impl.cu:269-270
-        uint32_t host_vals[2] = {0, 0};
-        GS2M_CUDA(cudaMemcpyAsync(&host_vals[0], g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (!force_v1) GS2M_CUDA(cudaMemcpyAsync(&host_vals[1], im.bin_info + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         GS2M_CUDA(cudaStreamSynchronize(s));
         if (host_vals[0] >= (1u << 30)) { set_error("%u Gaussian/tile instances exceed the supported 2^30", host_vals[0]); return GS2M_ERR_TOO_LARGE; }
         R = (int)host_vals[0];
-        max_tile_count = (int)host_vals[1];
+        if (path == BIN_DEPTHFIRST) V = (int)host_vals[1]; else max_tile_count = (int)host_vals[1];
+        if (path == BIN_RANKED && max_tile_count > GS2M_TILE_SORT_CAP) path = BIN_SORT64;   // a tile list too long for shared memory
     }
 
     char* bin_base = a->binning_buffer(a->binning_user, BinState::carve(nullptr, R, nullptr));
     if (!bin_base) { set_error("binning_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
     BinState b;
     BinState::carve(bin_base, R, &b);
-    const uint64_t* keys_sorted = b.keys_sorted;
-    point_list = b.point_list;
-    resolve_sorted(b, n_tiles, keys_sorted, point_list);
-    const bool use_v2 = !force_v1 && p.P > 0 && max_tile_count <= GS2M_TILE_SORT_CAP;
-    if (R > 0 && use_v2) {
-        // the final lists go where the 64-bit sort would have left them (see resolve_sorted); the other key buffer is scratch
-        uint64_t* keys_final = const_cast<uint64_t*>(keys_sorted);
-        uint32_t* vals_final = const_cast<uint32_t*>(point_list);
-        uint64_t* tmp = (keys_final == b.keys_sorted) ? b.keys_unsorted : b.keys_sorted;
-        StageTimer t(GS2M_STAGE_SORT, s);
-        rc = binning2_emit_and_sort(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, rank_order, tmp, keys_final, vals_final,
-                                    max_tile_count, s);
+    const uint32_t* point_list = b.point_list;
+    if (R > 0 && path == BIN_DEPTHFIRST) {
+        // depth order of the V visible Gaussians (ties keep ascending index: the compaction is stable and so is the sort)
+        int in_input = 0;
+        { StageTimer t(GS2M_STAGE_SORT, s);
+          rc = sort_pairs_u32_pingpong(g.depth_keys_alt, g.depth_keys, g.order_b, g.order_a, V, 32, g.rank_temp, s, &in_input); }
+        if (rc != GS2M_OK) return rc;
+        const uint32_t* order = in_input ? g.order_b : g.order_a;
+        // 32-bit tile ids ping-pong between the two halves of keys_unsorted; start where the last pass lands in point_list
+        int key_bits = 1;
+        while (((long long)n_tiles - 1) >> key_bits) ++key_bits;
+        uint32_t* tk[2] = {reinterpret_cast<uint32_t*>(b.keys_unsorted), reinterpret_cast<uint32_t*>(b.keys_unsorted) + R};
+        uint32_t* tv[2] = {b.vals_unsorted, b.point_list};
+        const int start = digit_passes(key_bits) & 1 ? 0 : 1;
+        { StageTimer t(GS2M_STAGE_DUPLICATE, s);
+          rc = binning_df_emit(V, g, order, a->out_radii, p.tiles_x, p.tiles_y, tk[start], tv[start], s); }
+        if (rc != GS2M_OK) return rc;
+        { StageTimer t(GS2M_STAGE_SORT, s);
+          rc = sort_pairs_u32_pingpong(tk[start], tk[start ^ 1], tv[start], tv[start ^ 1], R, key_bits, b.sort_temp, s, &in_input); }
+        if (rc != GS2M_OK) return rc;
+        if ((in_input != 0) != (start == 1)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
+        { StageTimer t(GS2M_STAGE_RANGES, s);
+          rc = launch_ranges_masks_keys(R, p.tiles_x, p.tiles_y, tk[1], point_list, g, b.keys_sorted, im.ranges, b.masks, s); }
+        if (rc != GS2M_OK) return rc;
+    } else if (R > 0 && path == BIN_RANKED) {
+        { StageTimer t(GS2M_STAGE_SORT, s);
+          rc = binning2_emit_and_sort(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, rank_order, b.keys_unsorted, b.keys_sorted,
+                                      b.point_list, max_tile_count, s); }
+        if (rc != GS2M_OK) return rc;
+        // the ranked path already wrote the tile ranges from its per-tile counts
+        { StageTimer t(GS2M_STAGE_RANGES, s); rc = launch_footprint_masks(p.tiles_x, p.tiles_y, im.ranges, point_list, g, b.masks, s); }
         if (rc != GS2M_OK) return rc;
     } else if (R > 0) {
+        const int key_bits = 32 + tile_bits((uint32_t)n_tiles);
+        uint64_t* kb[2] = {b.keys_unsorted, b.keys_sorted};
+        uint32_t* vb[2] = {b.vals_unsorted, b.point_list};
+        const int start = digit_passes(key_bits) & 1 ? 0 : 1;
         { StageTimer t(GS2M_STAGE_DUPLICATE, s);
-          rc = launch_duplicate_with_keys(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, b.keys_unsorted, b.vals_unsorted, s); }
+          rc = launch_duplicate_with_keys(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, kb[start], vb[start], s); }
         if (rc != GS2M_OK) return rc;
         int in_input = 0;
         { StageTimer t(GS2M_STAGE_SORT, s);
-          rc = sort_pairs_u64_pingpong(b.keys_unsorted, b.keys_sorted, b.vals_unsorted, b.point_list, R,
-                                       32 + tile_bits((uint32_t)n_tiles), b.sort_temp, s, &in_input); }
+          rc = sort_pairs_u64_pingpong(kb[start], kb[start ^ 1], vb[start], vb[start ^ 1], R, key_bits, b.sort_temp, s, &in_input); }
         if (rc != GS2M_OK) return rc;
-        if ((keys_sorted == b.keys_unsorted) != (in_input != 0)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
-    }
-    {
+        if ((in_input != 0) != (start == 1)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
+        // tile ranges + footprint masks in one pass over the sorted list
+        { StageTimer t(GS2M_STAGE_RANGES, s);
+          rc = launch_ranges_and_masks(R, p.tiles_x, p.tiles_y, b.keys_sorted, point_list, g, im.ranges, b.masks, s); }
+        if (rc != GS2M_OK) return rc;
+    } else {
         StageTimer t(GS2M_STAGE_RANGES, s);
-        if (use_v2 && p.P > 0) {   // the ranked path already wrote the tile ranges from its per-tile counts
-            if (R > 0) rc = launch_footprint_masks(p.tiles_x, p.tiles_y, im.ranges, point_list, g, b.masks, s);
-        } else if (p.P > 0) {      // tile ranges + footprint masks in one pass over the sorted list
-            rc = launch_ranges_and_masks(R, p.tiles_x, p.tiles_y, keys_sorted, point_list, g, im.ranges, b.masks, s);
-        } else {
-            rc = launch_identify_tile_ranges(0, keys_sorted, im.ranges, n_tiles, s);
-        }
+        rc = launch_identify_tile_ranges(0, b.keys_sorted, im.ranges, n_tiles, s);
         if (rc != GS2M_OK) return rc;
     }
     { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
@@ -338,9 +371,7 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     BinState::carve(a->binning_buffer, p.R, &b);
     ImageState im;
     ImageState::carve(a->image_buffer, p.W, p.H, &im);
-    const uint64_t* keys_sorted;
-    const uint32_t* point_list;
-    resolve_sorted(b, p.tiles_x * p.tiles_y, keys_sorted, point_list);
+    const uint32_t* point_list = b.point_list;
 
     { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, b.masks, im, s); }
     if (rc != GS2M_OK) return rc;
@@ -368,8 +399,8 @@ int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buff
     if (binning_buffer) {
         BinState b;
         BinState::carve(binning_buffer, R, &b);
-        const int tiles = ((width + GS2M_TILE_X - 1) / GS2M_TILE_X) * ((height + GS2M_TILE_Y - 1) / GS2M_TILE_Y);
-        resolve_sorted(b, tiles, out->keys_sorted, out->point_list);
+        out->keys_sorted = b.keys_sorted;
+        out->point_list = b.point_list;
     }
     if (image_buffer) {
         ImageState im;

@@ -15,6 +15,7 @@
 // ~32 B of traffic per instance.  Rectangles with more than 32 tiles are spread over the warp (the reference walks
 // them with one thread).  Tiles whose list exceeds the shared-memory capacity make the caller fall back to the global
 // 64-bit sort of binning.cu (same results).
+#include <atomic>
 #include "common.cuh"
 
 namespace gs2m {
@@ -260,8 +261,8 @@ int binning2_emit_and_sort(int P, const GeomState& g, const int* radii, int tile
     while ((1ll << key_bits) < (long long)P) ++key_bits;   // ranks are < P
     const int cap = ((max_count + 63) / 64) * 64;
     const size_t smem = tile_sort_smem_bytes(cap);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static std::atomic<size_t> configured{0};
+    if (smem > configured.load()) {
         GS2M_CUDA(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }

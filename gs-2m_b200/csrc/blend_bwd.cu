@@ -26,6 +26,7 @@
 //   accumulate                Lane g adds its 11+F sums to the Gaussian's packed 96-byte accumulator row with
 //                             128-bit vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4): 6 per
 //                             (Gaussian, warp block) instead of 21 x 32 scalar atomics.
+#include <atomic>
 #include "blend_common.cuh"
 
 namespace gs2m {
@@ -122,11 +123,17 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
     __syncwarp();
 }
 
-#ifndef GS2M_BWD_MINBLOCKS
-#define GS2M_BWD_MINBLOCKS 2
+// Warps are autonomous, so the CTA is only a scheduling unit: a tile's 8 warp blocks may be spread over 8 / GS2M_BWD_WARPS
+// CTAs (finer register-file granularity: occupancy is floor(64K / (regs * 32 * GS2M_BWD_WARPS)) CTAs).
+#ifndef GS2M_BWD_WARPS
+#define GS2M_BWD_WARPS 2
 #endif
+constexpr int BWD_CTA_WARPS = GS2M_BWD_WARPS;
+constexpr int BWD_CTAS_PER_TILE = BLEND_WARPS / BWD_CTA_WARPS;
+static_assert(BLEND_WARPS % BWD_CTA_WARPS == 0, "CTA must hold a divisor of the tile's 8 warp blocks");
+
 template <int F>
-__global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backward_kernel(
+__global__ void __launch_bounds__(BWD_CTA_WARPS * 32, 16 / BWD_CTA_WARPS) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
     int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -136,11 +143,12 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
     constexpr int NV = WarpSmemB<F>::NV;
     constexpr int NC = 3 + F;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpSmemB<F>& sm = reinterpret_cast<WarpSmemB<F>*>(smem_raw)[warp];
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(blockIdx.x % BWD_CTAS_PER_TILE) * BWD_CTA_WARPS + (int)(threadIdx.x >> 5);   // warp block in the tile
+    WarpSmemB<F>& sm = reinterpret_cast<WarpSmemB<F>*>(smem_raw)[threadIdx.x >> 5];
+    const int tile_x = blockIdx.x / BWD_CTAS_PER_TILE, tile_y = blockIdx.y;
     int px, py;
-    pixel_of_thread(tile_x, tile_y, tid, px, py);
+    pixel_of_thread(tile_x, tile_y, warp * 32 + lane, px, py);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
     const size_t N = (size_t)W * H;
@@ -309,15 +317,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, GS2M_BWD_MINBLOCKS) blend_backw
 template <int F>
 int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
              cudaStream_t s) {
-    dim3 grid(p.tiles_x, p.tiles_y);
-    const size_t smem = sizeof(WarpSmemB<F>) * BLEND_WARPS;
-    static bool configured = false;
+    dim3 grid(p.tiles_x * BWD_CTAS_PER_TILE, p.tiles_y);
+    const size_t smem = sizeof(WarpSmemB<F>) * BWD_CTA_WARPS;
+    static std::atomic<bool> configured{false};   // forward/backward may be driven from several host threads
     if (!configured) {
         GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     count_launches(1);
-    blend_backward_kernel<F><<<grid, BLEND_THREADS, smem, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
+    blend_backward_kernel<F><<<grid, BWD_CTA_WARPS * 32, smem, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                                g.conic_c_opac, g.rgb, p.features, p.background,
                                                                im.final_T, im.n_contrib, p.grad_color, p.grad_buffer,
                                                                g.grad_acc);

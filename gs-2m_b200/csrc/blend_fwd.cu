@@ -27,21 +27,30 @@ struct WarpSmemF {
     float4 col[NV][32];                         // r,g,b,f0 | f1..f4 | f5..f8 | f9,0,0,0
 };
 
+// Warps are autonomous, so the CTA is only a scheduling unit: a tile's 8 warp blocks are spread over 8 / GS2M_FWD_WARPS CTAs.
+#ifndef GS2M_FWD_WARPS
+#define GS2M_FWD_WARPS 1
+#endif
+constexpr int FWD_CTA_WARPS = GS2M_FWD_WARPS;
+constexpr int FWD_CTAS_PER_TILE = BLEND_WARPS / FWD_CTA_WARPS;
+static_assert(BLEND_WARPS % FWD_CTA_WARPS == 0, "CTA must hold a divisor of the tile's 8 warp blocks");
+
 template <int F>
-__global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
+__global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
     int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
     float* __restrict__ out_buffer) {
-    __shared__ WarpSmemF<F> sm_all[BLEND_WARPS];
+    __shared__ WarpSmemF<F> sm_all[FWD_CTA_WARPS];
     constexpr int NV = WarpSmemF<F>::NV;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpSmemF<F>& sm = sm_all[warp];
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(blockIdx.x % FWD_CTAS_PER_TILE) * FWD_CTA_WARPS + (int)(threadIdx.x >> 5);   // warp block in the tile
+    WarpSmemF<F>& sm = sm_all[threadIdx.x >> 5];
+    const int tile_x = blockIdx.x / FWD_CTAS_PER_TILE, tile_y = blockIdx.y;
     int px, py;
-    pixel_of_thread(tile_x, tile_y, tid, px, py);
+    pixel_of_thread(tile_x, tile_y, warp * 32 + lane, px, py);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
 
@@ -172,9 +181,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) blend_forward_kernel(
 template <int F>
 int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
              float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
-    dim3 grid(p.tiles_x, p.tiles_y);
+    dim3 grid(p.tiles_x * FWD_CTAS_PER_TILE, p.tiles_y);
     count_launches(1);
-    blend_forward_kernel<F><<<grid, BLEND_THREADS, 0, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
+    blend_forward_kernel<F><<<grid, FWD_CTA_WARPS * 32, 0, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                            g.conic_c_opac, g.rgb, p.features, p.background, im.final_T,
                                                            im.n_contrib, out_color, out_observe, out_buffer);
     GS2M_CUDA(cudaGetLastError());

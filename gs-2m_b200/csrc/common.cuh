@@ -91,6 +91,13 @@ int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int 
 int launch_identify_tile_ranges(int R, const uint64_t* keys_sorted, uint2* ranges, int n_tiles, cudaStream_t s);
 int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* keys_sorted, const uint32_t* point_list,
                             const GeomState& g, uint2* ranges, uint8_t* masks, cudaStream_t s);
+int launch_ranges_masks_keys(int R, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted, const uint32_t* point_list,
+                             const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks, cudaStream_t s);
+// depth-first binning (binning_depthfirst.cu)
+size_t compact_temp_bytes(int n);
+int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals, uint32_t* totals, cudaStream_t s);
+int binning_df_emit(int V, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x, int tiles_y,
+                    uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
 int launch_footprint_masks(int tiles_x, int tiles_y, const uint2* ranges, const uint32_t* point_list, const GeomState& g,
                            uint8_t* masks, cudaStream_t s);
 int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,

@@ -23,17 +23,22 @@ __global__ void __launch_bounds__(256) footprint_mask_kernel(int tiles_x, const 
 
 // Same masks, one thread per instance, fused with the tile-range identification of the 64-bit-sort path
 // (identifyTileRanges, rasterizer_impl.cu:108-129): the sorted key gives the tile, the sorted value the Gaussian.
-__global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R, int tiles_x, const uint64_t* __restrict__ keys,
+// KeyT = uint64_t: the reference's (tile << 32 | depth) keys.  KeyT = uint32_t: bare tile ids of the depth-first binning
+// path; the 64-bit key of every instance is then re-materialised into keys64_out (the parity surface of the sort).
+template <typename KeyT>
+__global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R, int tiles_x, const KeyT* __restrict__ keys,
                                                                const uint32_t* __restrict__ point_list,
                                                                const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
+                                                               const float* __restrict__ depths, uint64_t* __restrict__ keys64_out,
                                                                uint2* __restrict__ ranges, uint8_t* __restrict__ masks) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
-    const uint32_t tile = (uint32_t)(keys[i] >> 32);
+    constexpr int SHIFT = sizeof(KeyT) == 8 ? 32 : 0;
+    const uint32_t tile = (uint32_t)(keys[i] >> SHIFT);
     if (i == 0) {
         ranges[tile].x = 0;
     } else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> SHIFT);
         if (prev != tile) {
             ranges[prev].y = (uint32_t)i;
             ranges[tile].x = (uint32_t)i;
@@ -41,6 +46,7 @@ __global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R, int tiles_
     }
     if (i == R - 1) ranges[tile].y = (uint32_t)R;
     const uint32_t gid = point_list[i];
+    if (sizeof(KeyT) == 4) keys64_out[i] = ((uint64_t)tile << 32) | (uint64_t)__float_as_uint(__ldg(depths + gid));
     const CullRecord cr = make_cull_record(__ldg(rec_a + gid), __ldg(rec_b + gid));
     const int ty = (int)(tile / (uint32_t)tiles_x), tx = (int)(tile - (uint32_t)ty * (uint32_t)tiles_x);
     masks[i] = (uint8_t)warp_block_mask(cr, tx * GS2M_TILE_X, ty * GS2M_TILE_Y);
@@ -53,8 +59,21 @@ int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* key
     GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
     if (R > 0) {
         count_launches(1);
-        ranges_and_masks_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
-                                                                g.conic_c_opac, ranges, masks);
+        ranges_and_masks_kernel<uint64_t><<<(R + 255) / 256, 256, 0, s>>>(R, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
+                                                                          g.conic_c_opac, nullptr, nullptr, ranges, masks);
+        GS2M_CUDA(cudaGetLastError());
+    }
+    return GS2M_OK;
+}
+
+// depth-first binning: sorted 32-bit tile ids in, ranges + masks + the 64-bit (tile | depth) keys out
+int launch_ranges_masks_keys(int R, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted, const uint32_t* point_list,
+                             const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks, cudaStream_t s) {
+    GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
+    if (R > 0) {
+        count_launches(1);
+        ranges_and_masks_kernel<uint32_t><<<(R + 255) / 256, 256, 0, s>>>(R, tiles_x, tile_keys_sorted, point_list, g.xy_conic_ab,
+                                                                          g.conic_c_opac, g.depths, keys64_out, ranges, masks);
         GS2M_CUDA(cudaGetLastError());
     }
     return GS2M_OK;

@@ -12,6 +12,7 @@
 // Every element of every output tensor is written (zeros for culled Gaussians), so the caller never has to
 // zero-fill 344 B/Gaussian the way rasterize_points.cu:150-159 does.  With `accumulate` the nine user-visible
 // tensors are updated with += instead (several views summed before one all-reduce).
+#include <atomic>
 #include "common.cuh"
 
 namespace gs2m {
@@ -460,7 +461,7 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
     const int blocks = (p.P + 255) / 256;
     count_launches(1);
     if (p.M <= 16) {
-        static bool configured = false;
+        static std::atomic<bool> configured{false};
         if (!configured) {
             GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
             GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));

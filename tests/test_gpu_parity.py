@@ -113,17 +113,23 @@ def test_sh_degrees_and_coefficient_counts(dgr, ref, deg, M):
         assert err <= 5e-4, "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
 
 
-@pytest.mark.parametrize("path", ["ranked", "sort64"])
-def test_both_binning_paths_are_bit_exact(dgr, ref, path, monkeypatch):
-    """GS2M_BINNING selects duplicate + 64-bit onesweep sort (default) or depth-rank + per-tile shared-memory sort;
-    keys, lists and ranges must be bit-identical to the reference with either (includes warp-shared huge rectangles)."""
+@pytest.mark.parametrize("path", ["depthfirst", "ranked", "sort64"])
+def test_all_binning_paths_are_bit_exact(dgr, ref, path, monkeypatch):
+    """GS2M_BINNING selects depth sort + emission in depth order + tile sort (default), duplicate + 64-bit onesweep sort, or
+    depth-rank + per-tile shared-memory sort; keys, lists and ranges must be bit-identical to the reference with each
+    (includes huge rectangles, a one-tile image = 1 tile-key bit, a 256-tile image = one digit pass, and depth ties)."""
     monkeypatch.setenv("GS2M_BINNING", path)
-    for P, W, H, F, scale_big in ((60_000, 640, 400, 10, 1.0), (4_000, 330, 210, 5, 60.0)):
+    for P, W, H, F, scale_big in ((60_000, 640, 400, 10, 1.0), (4_000, 330, 210, 5, 60.0), (900, 16, 16, 3, 1.0),
+                                  (20_000, 256, 256, 2, 1.0)):
         scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
         if scale_big != 1.0:
             sc = scene.scales.clone()
             sc[:50] *= scale_big
             scene = scene._replace(scales=sc.contiguous())
+        if P == 20_000:   # exact depth ties between different Gaussians: the order inside a tile must fall back to the index
+            m = scene.means3D.clone()
+            m[1::2] = m[0::2]
+            scene = scene._replace(means3D=m.contiguous())
         r = helpers.run_reference(ref, scene, cam, feats, F)
         o = helpers.run_ours(dgr, scene, cam, feats, F)
         assert_forward_bit_exact(o, r, P)

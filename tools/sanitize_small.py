@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small forward+backward runs for compute-sanitizer (memcheck / racecheck / synccheck): both binning paths, a few F."""
+"""Small forward+backward runs for compute-sanitizer (memcheck / racecheck / synccheck): all binning paths, a few F."""
 import os
 import sys
 
@@ -11,7 +11,7 @@ for sub in ("gs-2m_b200", "oracle", "tests"):
 import helpers  # noqa: E402
 import diff_gaussian_rasterization as dgr  # noqa: E402
 
-for path in ("sort64", "ranked"):
+for path in ("depthfirst", "sort64", "ranked"):
     os.environ["GS2M_BINNING"] = path
     for (P, W, H, F) in ((1500, 100, 70, 10), (800, 64, 48, 5), (300, 33, 17, 0)):
         scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
