@@ -187,13 +187,15 @@ def run_ours(args, cfg, rank, world, device):
     copy_stream = torch.cuda.Stream(device=device)
     slots = [dict(gt=torch.empty((3, H, W), device=device), wvt=torch.empty((4, 4), device=device),
                   full=torch.empty((4, 4), device=device), cpos=torch.empty(3, device=device),
-                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2 * max(args.streams, 1))]
     h2d = sum(t.numel() * 4 for t in h_cam[my_views[0]]) + h_gt.numel() * 4
     d2h = 4
     seq = {"k": 0}
 
+    n_ahead = max(args.streams, 1)        # views in flight (one per stream); each view prefetches the one n_ahead later
+
     def prefetch(k, v):
-        sl = slots[k % 2]
+        sl = slots[k % len(slots)]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(sl["free"])
             sl["gt"].copy_(h_gt, non_blocking=True)
@@ -204,11 +206,12 @@ def run_ours(args, cfg, rank, world, device):
 
     def render_view_e2e(v, buckets, accumulate):
         k = seq["k"]
-        if k == 0:
-            prefetch(0, v)
         pos = my_views.index(v)
-        prefetch(k + 1, my_views[(pos + 1) % len(my_views)])
-        sl = slots[k % 2]
+        if k == 0:
+            for j in range(n_ahead):
+                prefetch(j, my_views[(pos + j) % len(my_views)])
+        prefetch(k + n_ahead, my_views[(pos + n_ahead) % len(my_views)])
+        sl = slots[k % len(slots)]
         torch.cuda.current_stream(device).wait_event(sl["ready"])
         st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, sl["wvt"],
                                                sl["full"], 3, sl["cpos"], False, F)
@@ -223,8 +226,8 @@ def run_ours(args, cfg, rank, world, device):
         seq["k"] = k + 1
         return {"radii": radii, "observe": observe}
 
-    step_e2e = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank)   # single stream: the
-    step_e2e.buckets = step.buckets                                   # prefetch pipeline above is written for one
+    step_e2e = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank, n_streams=args.streams)
+    step_e2e.bucket_sets, step_e2e.buckets = step.bucket_sets, step.buckets      # share the gradient buckets of the resident leg
     step_e2e.run(n_views)
     barrier()
     t0 = time.perf_counter()

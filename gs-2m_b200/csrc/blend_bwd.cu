@@ -47,41 +47,47 @@ struct WarpSmemB {
     float park_q[PARK * PARK_STRIDE];
 };
 
+__device__ __forceinline__ float __frcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // Reduce phase: lane (e = lane & 15, h = lane >> 4) owns parked entry e and sums over the 16 pixels of half h;
 // the two halves are combined with one shuffle per value and lanes 0..15 issue the vector reductions.
+// Only the Gaussian index of a parked entry is carried in registers (lane e holds entry e's); the 32-byte record is
+// re-gathered here (an L1/L2 hit) while the colour sums, which do not need it, are running.
+// The geometric sums are linear in the six moments sum(q), sum(q dx), sum(q dy), sum(q dx dx), sum(q dx dy),
+// sum(q dy dy); only the AbsGS sums need the per-pixel value.
 template <int F>
-__device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_parked, float4 ra, float2 rb, int gid,
+__device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_parked, int my_gid,
+                                              const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
                                               float wpx0, float wpy0, float half_w, float half_h,
                                               float* __restrict__ grad_acc) {
     constexpr int NV = WarpSmemB<F>::NV;
     constexpr int NC = 3 + F;
     constexpr int NG = 11 + F;
     const int e = lane & 15, h = lane >> 4;
-    // entry data lives in lane e's registers; give lane e+16 a copy
-    ra.x = __shfl_sync(0xffffffffu, ra.x, e); ra.y = __shfl_sync(0xffffffffu, ra.y, e);
-    ra.z = __shfl_sync(0xffffffffu, ra.z, e); ra.w = __shfl_sync(0xffffffffu, ra.w, e);
-    rb.x = __shfl_sync(0xffffffffu, rb.x, e); rb.y = __shfl_sync(0xffffffffu, rb.y, e);
-    const float gx = ra.x, gy = ra.y, ca = ra.z, cb = ra.w, cc = rb.x, op = rb.y;
+    const int gid = __shfl_sync(0xffffffffu, my_gid, e);
     float out[GS2M_ACC_STRIDE];
 #pragma unroll
     for (int i = 0; i < GS2M_ACC_STRIDE; ++i) out[i] = 0.f;
     if (e < n_parked) {
+        const float4 ra = __ldg(rec_a + gid);
+        const float4 rb = __ldg(rec_b + gid);
         float gc[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) gc[i] = 0.f;
-        float sx = 0.f, sy = 0.f, ax = 0.f, ay = 0.f, cxx = 0.f, cxy = 0.f, cyy = 0.f, so = 0.f;
         const float* pw = &sm.park_w[e * PARK_STRIDE + h * 16];
         const float* pq = &sm.park_q[e * PARK_STRIDE + h * 16];
         const float4* dp = sm.dpix[h];
-        const float py_half = wpy0 + (float)(2 * h);
 #pragma unroll 8
         for (int j = 0; j < 16; ++j) {
             const float w = pw[j];
-            const float q = pq[j];
             float d[4 * NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
@@ -90,26 +96,33 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
             }
 #pragma unroll
             for (int i = 0; i < NC; ++i) gc[i] = fmaf(w, d[i], gc[i]);
-            const float dx = gx - (wpx0 + (float)(j & 7));
-            const float dy = gy - (py_half + (float)(j >> 3));
-            const float qx = q * fmaf(ca, dx, cb * dy);
-            const float qy = q * fmaf(cc, dy, cb * dx);
-            sx += qx; sy += qy; ax += fabsf(qx); ay += fabsf(qy);
+        }
+        const float ca = ra.z, cb = ra.w, cc = rb.x, op = rb.y;
+        const float gxr = ra.x - wpx0;                         // exact: both are multiples of ulp(mean) and the result is smaller
+        const float gyr = ra.y - (wpy0 + (float)(2 * h));
+        float m0 = 0.f, mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f, ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float q = pq[j];
+            const float dx = gxr - (float)(j & 7);
+            const float dy = gyr - (float)(j >> 3);
             const float qdx = q * dx, qdy = q * dy;
-            cxx = fmaf(qdx, dx, cxx);
-            cxy = fmaf(qdx, dy, cxy);
-            cyy = fmaf(qdy, dy, cyy);
-            so += q;
+            m0 += q; mx += qdx; my += qdy;
+            mxx = fmaf(qdx, dx, mxx);
+            mxy = fmaf(qdx, dy, mxy);
+            myy = fmaf(qdy, dy, myy);
+            ax += fabsf(fmaf(ca, qdx, cb * qdy));
+            ay += fabsf(fmaf(cc, qdy, cb * qdx));
         }
         const float kx = op * half_w, ky = op * half_h;
-        out[0] = -kx * sx;
-        out[1] = -ky * sy;
+        out[0] = -kx * fmaf(ca, mx, cb * my);
+        out[1] = -ky * fmaf(cc, my, cb * mx);
         out[2] = fabsf(kx) * ax;
         out[3] = fabsf(ky) * ay;
-        out[4] = -0.5f * op * cxx;
-        out[5] = -0.5f * op * cxy;
-        out[6] = -0.5f * op * cyy;
-        out[7] = so;
+        out[4] = -0.5f * op * mxx;
+        out[5] = -0.5f * op * mxy;
+        out[6] = -0.5f * op * myy;
+        out[7] = m0;
 #pragma unroll
         for (int i = 0; i < NC; ++i) out[8 + i] = gc[i];
     }
@@ -128,12 +141,20 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
 #ifndef GS2M_BWD_WARPS
 #define GS2M_BWD_WARPS 2
 #endif
+#ifndef GS2M_BWD_WARPS_PER_SM
+#define GS2M_BWD_WARPS_PER_SM 20     // 96 registers per thread (4 bytes of spill); 16 (128 registers) is 6 % slower, 22 (88) 1.5 % slower
+#endif
 constexpr int BWD_CTA_WARPS = GS2M_BWD_WARPS;
 constexpr int BWD_CTAS_PER_TILE = BLEND_WARPS / BWD_CTA_WARPS;
 static_assert(BLEND_WARPS % BWD_CTA_WARPS == 0, "CTA must hold a divisor of the tile's 8 warp blocks");
 
+#ifdef GS2M_BWD_MAXNREG
+#define GS2M_BWD_BOUNDS __maxnreg__(GS2M_BWD_MAXNREG)
+#else
+#define GS2M_BWD_BOUNDS __launch_bounds__(BWD_CTA_WARPS * 32, GS2M_BWD_WARPS_PER_SM / BWD_CTA_WARPS)
+#endif
 template <int F>
-__global__ void __launch_bounds__(BWD_CTA_WARPS * 32, 16 / BWD_CTA_WARPS) blend_backward_kernel(
+__global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
     int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -189,8 +210,6 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, 16 / BWD_CTA_WARPS) blend_
 
     float S = 0.f, last_alpha = 0.f, last_cd = 0.f;
     int n_parked = 0, my_gid = 0;
-    float4 my_ra = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 my_rb = make_float2(0.f, 0.f);
 
     // software pipeline of the gathers (indices two steps ahead, records one step ahead)
     // (the footprint masks written by the forward say which entries reach this warp's block; only those lanes gather)
@@ -271,9 +290,12 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, 16 / BWD_CTA_WARPS) blend_
                 const float G = u ? G1 : G0;
                 float pw = 0.f, pq = 0.f;
                 if (v) {
-                    // one correctly-rounded reciprocal serves both T / (1 - alpha) and T_final / (1 - alpha)
-                    // (backward.cu:532,572 divide twice; the <= 1 ulp difference per step is far inside the 1e-4 gate)
-                    const float inv_one_m_alpha = __frcp_rn(1.0f - alpha);
+                    // one reciprocal serves both T / (1 - alpha) and T_final / (1 - alpha) (backward.cu:532,572 divide
+                    // twice).  1 - alpha is in [0.01, 1], so MUFU.RCP + one Newton step is within 1 ulp without the
+                    // range checks of a correctly rounded reciprocal; the difference is far inside the 1e-4 gate.
+                    const float one_m_alpha = 1.0f - alpha;
+                    float inv_one_m_alpha = __frcp_approx(one_m_alpha);
+                    inv_one_m_alpha = fmaf(inv_one_m_alpha, fmaf(-one_m_alpha, inv_one_m_alpha, 1.0f), inv_one_m_alpha);
                     T *= inv_one_m_alpha;
                     float c[4 * NV];
 #pragma unroll
@@ -292,16 +314,13 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, 16 / BWD_CTA_WARPS) blend_
                     pw = alpha * T;
                     pq = dL_dalpha * G;
                 }
-                if (lane == n_parked) {
-                    const float4 ra = u ? ra1 : ra0, rb = u ? rb1 : rb0;
-                    my_ra = ra; my_rb = make_float2(rb.x, rb.y); my_gid = __float_as_int(rb.z);
-                }
+                if (lane == n_parked) my_gid = __float_as_int(u ? rb1.z : rb0.z);
                 sm.park_w[n_parked * PARK_STRIDE + lane] = pw;
                 sm.park_q[n_parked * PARK_STRIDE + lane] = pq;
                 ++n_parked;
                 if (n_parked == PARK) {
                     __syncwarp();
-                    reduce_parked<F>(sm, lane, n_parked, my_ra, my_rb, my_gid, wpx0, wpy0, half_w, half_h, grad_acc);
+                    reduce_parked<F>(sm, lane, n_parked, my_gid, rec_a, rec_b, wpx0, wpy0, half_w, half_h, grad_acc);
                     n_parked = 0;
                 }
             }
@@ -310,7 +329,7 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, 16 / BWD_CTA_WARPS) blend_
     }
     if (n_parked > 0) {
         __syncwarp();
-        reduce_parked<F>(sm, lane, n_parked, my_ra, my_rb, my_gid, wpx0, wpy0, half_w, half_h, grad_acc);
+        reduce_parked<F>(sm, lane, n_parked, my_gid, rec_a, rec_b, wpx0, wpy0, half_w, half_h, grad_acc);
     }
 }
 
@@ -322,6 +341,9 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
     static std::atomic<bool> configured{false};   // forward/backward may be driven from several host threads
     if (!configured) {
         GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef GS2M_BWD_CARVEOUT
+        GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributePreferredSharedMemoryCarveout, GS2M_BWD_CARVEOUT));
+#endif
         configured = true;
     }
     count_launches(1);
