@@ -18,6 +18,12 @@
 namespace gs2m {
 namespace {
 
+// accumulate mode adds with fire-and-forget vector reductions (red.global.add.v4.f32): the read-modify-write happens in
+// L2, so the store phase of a block has no load latency to wait for
+__device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <bool ACC>
 __device__ __forceinline__ void put(float* p, float v) {
     if (ACC) *p += v; else *p = v;
@@ -333,11 +339,11 @@ struct StagedIO {
     __device__ StagedIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
     __device__ void mean2d(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
-        if (ACC) { float4 u = *o; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
-        *o = v;
+        if (ACC) red_add_f4(o, v);
+        else *o = v;
     }
     __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
-    __device__ void opacity(float v) { put<ACC>(p.dL_dopacity + i, v); }
+    __device__ void opacity(float v) { if (ACC) atomicAdd(p.dL_dopacity + i, v); else p.dL_dopacity[i] = v; }
     __device__ void color(int k, float v) { sm.color[t * ST_V3 + k] = v; }
     __device__ void feature(int k, float v) { sm.feat[t * ST_FEAT + k] = v; }
     __device__ void mean3d(int k, float v) { sm.mean3d[t * ST_V3 + k] = v; }
@@ -345,8 +351,8 @@ struct StagedIO {
     __device__ void scale(int k, float v) { sm.scale[t * ST_V3 + k] = v; }
     __device__ void rot(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
-        if (ACC) { float4 u = *o; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
-        *o = v;
+        if (ACC) red_add_f4(o, v);
+        else *o = v;
     }
     __device__ float sh_in(int k) const { return sm.sh[t * sh_row + k]; }
     __device__ void sh_out(int k, float v) { sm.sh[t * sh_row + k] = v; }
@@ -364,16 +370,17 @@ __device__ __forceinline__ void block_store(float* __restrict__ dst, const float
         float4 v = s4[e];
         if (ACC) {
             // rows of culled Gaussians hold no staged values in accumulate mode: mask them out element-wise
-            const float4 u = d4[e];
-            v.x = vis[(4 * e) / ROW] ? v.x + u.x : u.x;
-            v.y = vis[(4 * e + 1) / ROW] ? v.y + u.y : u.y;
-            v.z = vis[(4 * e + 2) / ROW] ? v.z + u.z : u.z;
-            v.w = vis[(4 * e + 3) / ROW] ? v.w + u.w : u.w;
+            v.x = vis[(4 * e) / ROW] ? v.x : 0.f;
+            v.y = vis[(4 * e + 1) / ROW] ? v.y : 0.f;
+            v.z = vis[(4 * e + 2) / ROW] ? v.z : 0.f;
+            v.w = vis[(4 * e + 3) / ROW] ? v.w : 0.f;
+            red_add_f4(d4 + e, v);
+        } else {
+            d4[e] = v;
         }
-        d4[e] = v;
     }
     for (int e = (n4 << 2) + threadIdx.x; e < n; e += 256) {
-        if (ACC) { if (vis[e / ROW]) dst[e] += src[e]; }
+        if (ACC) { if (vis[e / ROW]) atomicAdd(dst + e, src[e]); }
         else dst[e] = src[e];
     }
 }
@@ -435,8 +442,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
                 const float* q = sm.sh + r * sh_pad + c;
                 float4 v = make_float4(q[0], q[1], q[2], q[3]);
                 float4* d4 = reinterpret_cast<float4*>(dst) + e4;
-                if (ACC) { const float4 u = *d4; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
-                *d4 = v;
+                if (ACC) red_add_f4(d4, v);
+                else *d4 = v;
             }
         } else {
             for (int e = t; e < n; e += 256) {
