@@ -235,7 +235,7 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         if (!geom_base) { set_error("geometry_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
         GeomState::carve(geom_base, p.P, &g);
 
-        { StageTimer t(GS2M_STAGE_PREPROCESS_FWD, s); rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, s); }
+        { StageTimer t(GS2M_STAGE_PREPROCESS_FWD, s); rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, path == BIN_RANKED, s); }
         if (rc != GS2M_OK) return rc;
         uint32_t host_vals[2] = {0, 0};
         if (path == BIN_DEPTHFIRST) {

@@ -84,7 +84,7 @@ struct FwdParams {
     const float *viewmatrix, *projmatrix, *cam_pos, *background;
 };
 
-int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, cudaStream_t s);
+int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, bool rank_keys, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y,
                                uint64_t* keys, uint32_t* vals, cudaStream_t s);

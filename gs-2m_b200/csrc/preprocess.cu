@@ -122,19 +122,33 @@ __device__ __forceinline__ void sh_to_rgb(int D, float x, float y, float z, Load
     }
 }
 
+// RANK_KEYS: also write the (depth bits, iota) pairs the "ranked" binning path sorts (binning_v2.cu)
+template <bool RANK_KEYS>
 __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, GeomState g, int* __restrict__ radii,
                                                                  int* __restrict__ observe) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
 
+    // every load that does not depend on the culling decision is issued up front, next to the position's
+    const float px = p.means3D[3 * idx + 0], py = p.means3D[3 * idx + 1], pz = p.means3D[3 * idx + 2];
+    const float opacity = p.opacities[idx];
+    float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.cov3D_precomp == nullptr) {
+        const float* sc = p.scales + 3 * (size_t)idx;
+        sc0 = sc[0]; sc1 = sc[1]; sc2 = sc[2];
+        q = *reinterpret_cast<const float4*>(p.rotations + 4 * (size_t)idx);
+    }
+
     // outputs every Gaussian gets, visible or not
     radii[idx] = 0;
     observe[idx] = 0;
     g.tiles_touched[idx] = 0;
-    g.depth_keys[idx] = 0xFFFFFFFFu;   // culled Gaussians rank behind every visible one
-    g.order_a[idx] = (uint32_t)idx;
+    if (RANK_KEYS) {
+        g.depth_keys[idx] = 0xFFFFFFFFu;   // culled Gaussians rank behind every visible one
+        g.order_a[idx] = (uint32_t)idx;
+    }
 
-    const float px = p.means3D[3 * idx + 0], py = p.means3D[3 * idx + 1], pz = p.means3D[3 * idx + 2];
     const float* __restrict__ vm = p.viewmatrix;
     const float* __restrict__ pm = p.projmatrix;
 
@@ -154,9 +168,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
         const float* c = p.cov3D_precomp + 6 * (size_t)idx;
         S.c0 = c[0]; S.c1 = c[1]; S.c2 = c[2]; S.c3 = c[3]; S.c4 = c[4]; S.c5 = c[5];
     } else {
-        const float* sc = p.scales + 3 * (size_t)idx;
-        const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * (size_t)idx);
-        S = covariance_from_scale_rotation(sc[0], sc[1], sc[2], p.scale_modifier, q.x, q.y, q.z, q.w);
+        S = covariance_from_scale_rotation(sc0, sc1, sc2, p.scale_modifier, q.x, q.y, q.z, q.w);
         float* o = g.cov3D + 6 * (size_t)idx;
         o[0] = S.c0; o[1] = S.c1; o[2] = S.c2; o[3] = S.c3; o[4] = S.c4; o[5] = S.c5;
     }
@@ -222,7 +234,20 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
         const float ux = __fdiv_rn(dx, len), uy = __fdiv_rn(dy, len), uz = __fdiv_rn(dz, len);
         const float* __restrict__ shp = p.shs + (size_t)idx * p.M * 3;
         float res[3];
-        sh_to_rgb(p.D, ux, uy, uz, [&](int k, int c) { return __ldg(shp + 3 * k + c); }, res);
+        if (((3 * p.M) & 3) == 0) {
+            // rows are 16-byte aligned: fetch the (D+1)^2 x 3 coefficients with 128-bit loads, all in flight at once
+            float c[48];
+            const int n4 = (3 * (p.D + 1) * (p.D + 1) + 3) >> 2;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n4) t = __ldg(reinterpret_cast<const float4*>(shp) + i);
+                c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w;
+            }
+            sh_to_rgb(p.D, ux, uy, uz, [&](int k, int ch) { return c[3 * k + ch]; }, res);
+        } else {
+            sh_to_rgb(p.D, ux, uy, uz, [&](int k, int ch) { return __ldg(shp + 3 * k + ch); }, res);
+        }
         uchar4 cl;
         cl.x = !(res[0] >= -0.5f); cl.y = !(res[1] >= -0.5f); cl.z = !(res[2] >= -0.5f); cl.w = 0;
         rgb.x = cl.x ? 0.f : __fadd_rn(res[0], 0.5f);
@@ -234,13 +259,12 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
         rgb.x = c[0]; rgb.y = c[1]; rgb.z = c[2];
     }
 
-    const float opacity = p.opacities[idx];
     // Footprint threshold for the blend kernels' conservative culling: a pixel can only receive
     // alpha >= 1/255 where  conic-quadratic q(d) <= 2*ln(255*opacity).  Negative => can never contribute.
     const float thr = (opacity >= 0.00392156885936856f) ? 2.0f * logf(255.0f * opacity) : -1.0f;
 
     g.depths[idx] = depth;
-    g.depth_keys[idx] = __float_as_uint(depth);
+    if (RANK_KEYS) g.depth_keys[idx] = __float_as_uint(depth);
     radii[idx] = radius;
     g.xy_conic_ab[idx] = make_float4(pix_x, pix_y, conic_x, conic_y);
     g.conic_c_opac[idx] = make_float4(conic_z, opacity, thr, 0.0f);
@@ -259,10 +283,11 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 }  // namespace
 
-int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, cudaStream_t s) {
+int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, bool rank_keys, cudaStream_t s) {
     if (p.P == 0) return GS2M_OK;
     count_launches(1);
-    preprocess_forward_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe);
+    if (rank_keys) preprocess_forward_kernel<true><<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe);
+    else preprocess_forward_kernel<false><<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }
