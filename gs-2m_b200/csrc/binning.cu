@@ -188,7 +188,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __r
                                                                  volatile uint32_t* __restrict__ status /*[tiles][256]*/,
                                                                  uint32_t* __restrict__ ticket) {
     __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];
-    __shared__ uint32_t s_base[RS_RADIX];
+    __shared__ uint32_t s_base[RS_RADIX];       // global index of the tile's first key of a digit, minus its tile-local offset
+    __shared__ uint32_t s_tile_off[RS_RADIX];   // tile-local offset of a digit's keys in the staged order
+    __shared__ uint32_t s_scan[8];
+    __shared__ KeyT s_keys[RS_TILE];            // the tile in sorted order: scattered here first, then copied out so that
+    __shared__ uint32_t s_vals[RS_TILE];        // keys of one digit leave as contiguous runs (coalesced sectors)
     __shared__ uint32_t s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
@@ -199,11 +203,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __r
     const int tile_start = (int)tile * RS_TILE + warp * 32 * RS_ITEMS;
 
     KeyT key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
     uint32_t rank[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const int g = tile_start + i * 32 + lane;
         key[i] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;
+        val[i] = (g < n) ? vals_in[g] : 0u;
     }
     // rank inside the warp, item by item (stable)
 #pragma unroll
@@ -253,18 +259,35 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __r
             }
             *st = RS_FLAG_PREFIX | (exclusive + count);
         }
-        s_base[d] = digit_base[d] + exclusive;
+        uint32_t tile_total;
+        const uint32_t tile_off = block_exclusive_scan(count, s_scan, tile_total);
+        s_tile_off[d] = tile_off;
+        s_base[d] = digit_base[d] + exclusive - tile_off;
     }
     __syncthreads();
 
+    // stage the tile in sorted order in shared memory ...
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const int g = tile_start + i * 32 + lane;
         if (g < n) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-            const uint32_t dst = s_base[d] + s_warp_hist[warp][d] + rank[i];
-            keys_out[dst] = key[i];
-            vals_out[dst] = vals_in[g];
+            const uint32_t pos = s_tile_off[d] + s_warp_hist[warp][d] + rank[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];
+        }
+    }
+    __syncthreads();
+    // ... and copy it out: consecutive threads hold consecutive keys of a digit, which are consecutive in the output
+    const int n_tile = min(RS_TILE, n - (int)tile * RS_TILE);
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int pos = i * RS_THREADS + threadIdx.x;
+        if (pos < n_tile) {
+            const KeyT k = s_keys[pos];
+            const uint32_t dst = s_base[(uint32_t)(k >> shift) & mask] + (uint32_t)pos;
+            keys_out[dst] = k;
+            vals_out[dst] = s_vals[pos];
         }
     }
 }
