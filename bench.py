@@ -120,11 +120,12 @@ def run_ours(args, cfg, rank, world, device):
         color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
                                                                scene.scales, scene.rotations, None, feats[v], st)
         dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], radii,
-                         st, state, grads=buckets.tensors, accumulate=accumulate)
+                         st, state, grads=buckets.tensors, accumulate=accumulate, densify_stats=holder["step"].stats.backward_args())
         stats["R"], stats["radii"] = state.num_rendered, radii
         return {"radii": radii, "observe": observe}
 
-    step = vp.ViewShardedStep(P, M, device, render_view, world=world, rank=rank, n_streams=args.streams)
+    holder = {}
+    step = holder["step"] = vp.ViewShardedStep(P, M, device, render_view, world=world, rank=rank, n_streams=args.streams)
 
     def barrier():
         if world > 1:
@@ -221,12 +222,13 @@ def run_ours(args, cfg, rank, world, device):
         h_loss[pos].copy_((diff * diff).mean(), non_blocking=True)
         grad_c = diff * (2.0 / diff.numel())
         dgr.backward_raw(grad_c, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v],
-                         radii, st, state, grads=buckets.tensors, accumulate=accumulate)
+                         radii, st, state, grads=buckets.tensors, accumulate=accumulate,
+                         densify_stats=holder["e2e"].stats.backward_args())
         sl["free"].record(torch.cuda.current_stream(device))
         seq["k"] = k + 1
         return {"radii": radii, "observe": observe}
 
-    step_e2e = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank, n_streams=args.streams)
+    step_e2e = holder["e2e"] = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank, n_streams=args.streams)
     step_e2e.bucket_sets, step_e2e.buckets = step.bucket_sets, step.buckets      # share the gradient buckets of the resident leg
     step_e2e.run(n_views)
     barrier()

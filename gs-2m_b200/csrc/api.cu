@@ -364,6 +364,8 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     p.dL_dmeans2D = a->dL_dmeans2D; p.dL_dconic = a->dL_dconic; p.dL_dopacity = a->dL_dopacity; p.dL_dcolor = a->dL_dcolor;
     p.dL_dmeans3D = a->dL_dmeans3D; p.dL_dcov3D = a->dL_dcov3D; p.dL_dsh = a->dL_dsh; p.dL_dscale = a->dL_dscale;
     p.dL_drot = a->dL_drot; p.dL_dfeatures = a->dL_dfeatures; p.accumulate = a->accumulate;
+    p.densify_grad_accum = a->densify_grad_accum; p.densify_grad_accum_abs = a->densify_grad_accum_abs;
+    p.densify_denom = a->densify_denom;
 
     GeomState g;
     GeomState::carve(a->geometry_buffer, p.P, &g);

@@ -76,6 +76,18 @@ __global__ void __launch_bounds__(256) postblend_backward_kernel(PostIn in, cons
     for (int c = 5; c < GS2M_NUM_FEATURES; ++c) g_buffer[c * N + i] = 0.f;
 }
 
+// train.py:225-228 and :238-241 on one view's (radii, observe)
+__global__ void __launch_bounds__(256) view_stats_kernel(int P, const int* __restrict__ radii, const int* __restrict__ observe,
+                                                         float* __restrict__ max_radii2D, float* __restrict__ observe_cnt) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    const int r = radii[i];
+    if (observe[i] <= 0) return;
+    if (observe_cnt) atomicAdd(observe_cnt + i, 1.0f);
+    // non-negative floats order like their bit patterns
+    if (max_radii2D && r > 0) atomicMax(reinterpret_cast<int*>(max_radii2D) + i, __float_as_int((float)r));
+}
+
 }  // namespace
 }  // namespace gs2m
 
@@ -107,6 +119,15 @@ int gs2m_postblend_backward(int width, int height, float fx, float fy, float cx,
     const size_t N = (size_t)width * height;
     count_launches(1);
     postblend_backward_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, dL_dlocal_normal_map, dL_ddepth_map, dL_dbuffer);
+    GS2M_CUDA(cudaGetLastError());
+    return GS2M_OK;
+}
+
+int gs2m_view_stats_update(int P, const int* radii, const int* observe, float* max_radii2D, float* observe_cnt, void* stream) {
+    if (P < 0 || (P > 0 && (!radii || !observe))) { set_error("view_stats_update: bad arguments"); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (P == 0 || (!max_radii2D && !observe_cnt)) return GS2M_OK;
+    count_launches(1);
+    view_stats_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, radii, observe, max_radii2D, observe_cnt);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }

@@ -58,6 +58,11 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 
     // ---- pass-through gradients ----
     io.mean2d(make_float4(acc[0], acc[1], acc[2], acc[3]));
+    if (visible) {   // add_densification_stats (scene/gaussian_model.py:569-573), on this view's gradient
+        if (p.densify_grad_accum) atomicAdd(p.densify_grad_accum + idx, sqrtf(acc[0] * acc[0] + acc[1] * acc[1]));
+        if (p.densify_grad_accum_abs) atomicAdd(p.densify_grad_accum_abs + idx, sqrtf(acc[2] * acc[2] + acc[3] * acc[3]));
+        if (p.densify_denom) atomicAdd(p.densify_denom + idx, 1.0f);
+    }
     io.conic(make_float4(acc[4], acc[5], 0.f, acc[6]));
     io.opacity(acc[7]);
     io.color(0, acc[8]); io.color(1, acc[9]); io.color(2, acc[10]);

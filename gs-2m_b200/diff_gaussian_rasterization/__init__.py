@@ -169,9 +169,11 @@ def alloc_grads(P, M, device, zero=False):
 
 def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features,
                  radii, raster_settings: GaussianRasterizationSettings, state: RasterState, grads=None,
-                 accumulate=False):
+                 accumulate=False, densify_stats=None):
     """Run the backward pipeline into ``grads`` (dict from :func:`alloc_grads`; allocated when None).
-    With ``accumulate=True`` the nine caller-visible tensors are updated with ``+=``."""
+    With ``accumulate=True`` the nine caller-visible tensors are updated with ``+=``.
+    ``densify_stats = (xyz_gradient_accum, xyz_gradient_accum_abs, denom)`` (float ``[P]`` / ``[P,1]`` CUDA tensors, any may be
+    None) are updated like ``GaussianModel.add_densification_stats`` with this view's screen-space gradient."""
     lib = _native.load()
     dev = means3D.device
     rs = raster_settings
@@ -223,8 +225,30 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
         b.dL_dsh = _ptr(grads["dL_dsh"]) if M > 0 else None
         b.accumulate = int(bool(accumulate))
         b.stream = torch.cuda.current_stream(dev).cuda_stream
+        if densify_stats is not None:
+            for t in densify_stats:
+                if t is not None and (t.dtype != torch.float32 or t.numel() != P or not t.is_contiguous() or t.device != dev):
+                    raise RuntimeError("densify_stats tensors must be contiguous float32 with P elements on the inputs' device")
+            b.densify_grad_accum, b.densify_grad_accum_abs, b.densify_denom = (_ptr(t) for t in densify_stats)
         _native.check(lib.gs2m_rasterize_backward(b), "gs2m_rasterize_backward")
     return grads
+
+
+def update_view_stats(radii, observe, max_radii2D=None, observe_cnt=None):
+    """Per-view densification statistics of the forward outputs, fused (train.py:225-228, 238-241):
+    ``max_radii2D = where((observe > 0) & (radii > 0), max(max_radii2D, radii), max_radii2D)``; ``observe_cnt[observe > 0] += 1``."""
+    lib = _native.load()
+    dev = radii.device
+    if not radii.is_cuda:
+        raise RuntimeError("update_view_stats has no CPU path: radii must be a CUDA tensor")
+    P = int(radii.numel())
+    for t in (max_radii2D, observe_cnt):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != P or not t.is_contiguous() or t.device != dev):
+            raise RuntimeError("statistics tensors must be contiguous float32 with P elements on the inputs' device")
+    with torch.cuda.device(dev):
+        _native.check(lib.gs2m_view_stats_update(P, _ptr(radii.contiguous()), _ptr(observe.contiguous()), _ptr(max_radii2D),
+                                                 _ptr(observe_cnt), torch.cuda.current_stream(dev).cuda_stream),
+                      "gs2m_view_stats_update")
 
 
 def state_view(P, raster_settings, state: RasterState):

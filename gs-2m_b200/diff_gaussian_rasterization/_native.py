@@ -56,6 +56,7 @@ class BackwardArgs(C.Structure):
         ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscale", _fp), ("dL_drot", _fp), ("dL_dfeatures", _fp),
         ("accumulate", C.c_int),
         ("stream", C.c_void_p),
+        ("densify_grad_accum", _fp), ("densify_grad_accum_abs", _fp), ("densify_denom", _fp),
     ]
 
 
@@ -84,6 +85,7 @@ EXPORTS = [
     ("gs2m_pack_backward", C.c_int, [C.c_int] + [_fp] * 9 + [C.c_int, C.c_int] + [_fp] * 11 + [C.c_void_p]),
     ("gs2m_postblend_forward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
     ("gs2m_postblend_backward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
+    ("gs2m_view_stats_update", C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]),
     ("gs2m_profile_enable", None, [C.c_int]),
     ("gs2m_profile_read", C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("gs2m_launch_count", C.c_longlong, []),
@@ -116,7 +118,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the header and the library diverge
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.gs2m_abi_version() != 1:
+    if lib.gs2m_abi_version() != 2:
         raise ImportError("libgs2m_rasterizer.so ABI version mismatch")
     _lib = lib
     return lib

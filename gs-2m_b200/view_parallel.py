@@ -9,8 +9,9 @@ module does the same sum across a *batch* of views and across ranks:
 * ``GradientBuckets``                    – the dense per-Gaussian gradient tensors (reference shapes,
   rasterize_points.cu:150-159).  A rank's views accumulate into them in place (the C-ABI's ``accumulate`` flag, so
   there is no per-view zero-fill or extra add kernel); one ``all_reduce(SUM)`` per tensor then makes every rank hold
-  the batch gradient.  Densification statistics need the same reduction (SUM for the .zw |grad| columns of
-  ``dL_dmeans2D``, MAX for radii, SUM>0 for observe; train.py:225-245) and are covered by ``reduce_statistics``.
+  the batch gradient.
+* ``DensificationStats``                 – GS-2M's densification bookkeeping (max_radii2D, xyz_gradient_accum{,_abs}, denom,
+  observe_cnt; train.py:225-245, scene/gaussian_model.py:569-573) with fused per-view updates, MAX / SUM all-reduced.
 * ``ViewShardedStep``                    – runs forward+backward for this rank's views through a caller-supplied
   ``render_view`` callable and finishes with the all-reduce.  The callable is the only piece that touches CUDA, so
   the sharding / accumulation / reduction logic is testable on CPU with the gloo backend.
@@ -87,14 +88,58 @@ class GradientBuckets:
         return [work] if async_op else []
 
 
-def reduce_statistics(radii_max: torch.Tensor, observe_count: torch.Tensor):
-    """Densification bookkeeping that also has to agree on every rank: screen radii are MAX-reduced
-    (scene/gaussian_model.py max_radii2D, train.py:226) and the per-view ``observe > 0`` hit counts are SUM-reduced
-    (train.py:238-243)."""
-    if _dist_ready():
-        dist.all_reduce(radii_max, op=dist.ReduceOp.MAX)
-        dist.all_reduce(observe_count, op=dist.ReduceOp.SUM)
-    return radii_max, observe_count
+class DensificationStats:
+    """GS-2M's densification bookkeeping for one step, reference semantics and dtypes (float tensors):
+
+    * ``max_radii2D [P]``            ``where((observe > 0) & (radii > 0), max(., radii), .)``      train.py:225-227   MAX over ranks
+    * ``xyz_gradient_accum [P,1]``   ``+= |dL_dmeans2D.xy|`` per view, visible Gaussians          gaussian_model.py:569-571   SUM
+    * ``xyz_gradient_accum_abs``     ``+= |dL_dmeans2D.zw|`` (AbsGS)                               :572   SUM
+    * ``denom [P,1]``                ``+= 1`` per view, visible Gaussians                          :573   SUM
+    * ``observe_cnt [P,1]``          ``[observe > 0] += 1`` per view (multi-view trim)             train.py:238-241   SUM
+
+    All five are views of one flat buffer: one MAX and one SUM all-reduce.  On CUDA the per-view updates are fused into the
+    library (``update_view_stats`` after the forward; the gradient norms inside the backward, which sees the view's own
+    gradient even when the buckets accumulate) and are atomic, so views on different streams may share the buffers.
+    On CPU (gloo tests of the reduction logic) the same updates are plain torch ops.
+    """
+
+    def __init__(self, P: int, device):
+        self.P = P
+        self.flat = torch.zeros(5 * max(P, 1), dtype=torch.float32, device=device)
+        self.max_radii2D = self.flat[0:P]
+        self.xyz_gradient_accum = self.flat[P:2 * P].view(P, 1)
+        self.xyz_gradient_accum_abs = self.flat[2 * P:3 * P].view(P, 1)
+        self.denom = self.flat[3 * P:4 * P].view(P, 1)
+        self.observe_cnt = self.flat[4 * P:5 * P].view(P, 1)
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def backward_args(self):
+        """``densify_stats`` argument of ``backward_raw``."""
+        return (self.xyz_gradient_accum, self.xyz_gradient_accum_abs, self.denom)
+
+    def update_forward(self, radii: torch.Tensor, observe: torch.Tensor):
+        if radii.is_cuda:
+            import diff_gaussian_rasterization as dgr
+            dgr.update_view_stats(radii, observe, self.max_radii2D, self.observe_cnt.view(-1))
+        else:
+            seen = observe > 0
+            mask = seen & (radii > 0)
+            torch.where(mask, torch.maximum(self.max_radii2D, radii.to(torch.float32)), self.max_radii2D, out=self.max_radii2D)
+            self.observe_cnt.view(-1)[seen] += 1
+
+    def update_backward_eager(self, means2D_grad: torch.Tensor, radii: torch.Tensor):
+        """``add_densification_stats`` with torch ops (callers that do not use the fused path)."""
+        vis = radii > 0
+        self.xyz_gradient_accum[vis] += torch.norm(means2D_grad[vis, :2], dim=-1, keepdim=True)
+        self.xyz_gradient_accum_abs[vis] += torch.norm(means2D_grad[vis, 2:], dim=-1, keepdim=True)
+        self.denom[vis] += 1
+
+    def all_reduce(self):
+        if _dist_ready():
+            dist.all_reduce(self.flat[:self.P], op=dist.ReduceOp.MAX)
+            dist.all_reduce(self.flat[self.P:], op=dist.ReduceOp.SUM)
 
 
 class ViewShardedStep:
@@ -102,8 +147,10 @@ class ViewShardedStep:
 
     ``render_view(view_index, buckets, accumulate) -> dict`` must run forward+backward of one view, adding its
     gradients into ``buckets.tensors`` (``accumulate`` is False for the first view that writes a bucket set: the kernels
-    then overwrite, which saves zero-filling), and may return per-view statistics
-    ``{"radii": int32[P], "observe": int32[P]}``.
+    then overwrite, which saves zero-filling), and may return the view's ``{"radii": int32[P], "observe": int32[P]}`` for
+    the densification statistics in ``self.stats`` (:class:`DensificationStats`); to get the gradient-norm statistics it
+    passes ``densify_stats=step.stats.backward_args()`` to ``backward_raw`` (or returns ``"means2D_grad"``, the view's own
+    ``[P,4]`` gradient, for the eager update).
 
     With ``n_streams > 1`` (CUDA only) consecutive views of a rank are issued round-robin on that many streams, each with
     its own bucket set, so the kernels of view k+1 fill the GPU while view k sits in the forward's instance-count
@@ -121,53 +168,46 @@ class ViewShardedStep:
         self.buckets = self.bucket_sets[0]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)] if use_streams else [None]
         self.render_view = render_view
-        self.radii_max = torch.zeros(P, dtype=torch.int32, device=device)
-        self.observe_count = torch.zeros(P, dtype=torch.int32, device=device)
+        self.stats = DensificationStats(P, device)
 
     def local_views(self, n_views: int) -> List[int]:
         return list(shard_views(n_views, self.world, self.rank))
 
-    def _one_view(self, v, buckets, accumulate, radii_max, observe_count):
-        stats = self.render_view(v, buckets, accumulate)
-        if stats:
-            if "radii" in stats:
-                torch.maximum(radii_max, stats["radii"], out=radii_max)
-            if "observe" in stats:
-                observe_count += (stats["observe"] > 0).to(torch.int32)
+    def _one_view(self, v, buckets, accumulate):
+        out = self.render_view(v, buckets, accumulate)
+        if out and "radii" in out and "observe" in out:
+            self.stats.update_forward(out["radii"], out["observe"])
+            if "means2D_grad" in out:
+                self.stats.update_backward_eager(out["means2D_grad"], out["radii"])
 
     def run(self, n_views: int, reduce: bool = True) -> Dict[str, torch.Tensor]:
         mine = self.local_views(n_views)
-        self.radii_max.zero_()
-        self.observe_count.zero_()
+        self.stats.zero_()
         if not mine:  # more ranks than views: contribute zeros
             self.buckets.zero_()
         if self.n_streams == 1:
             for k, v in enumerate(mine):
-                self._one_view(v, self.buckets, k > 0, self.radii_max, self.observe_count)
+                self._one_view(v, self.buckets, k > 0)
                 self.buckets.views_accumulated = k + 1
         else:
             main = torch.cuda.current_stream(self.device)
             ready = torch.cuda.Event()
             ready.record(main)
-            stats = [(torch.zeros_like(self.radii_max), torch.zeros_like(self.observe_count)) for _ in self.streams]
             used = min(self.n_streams, len(mine))
             for k, v in enumerate(mine):
                 j = k % self.n_streams
                 with torch.cuda.stream(self.streams[j]):
                     if k < self.n_streams:
                         self.streams[j].wait_event(ready)        # inputs / previous step's consumers are done
-                    self._one_view(v, self.bucket_sets[j], k >= self.n_streams, stats[j][0], stats[j][1])
+                    self._one_view(v, self.bucket_sets[j], k >= self.n_streams)   # statistics updates are atomic
             for j in range(used):
                 main.wait_stream(self.streams[j])
-            for j in range(used):                                   # fold the per-stream partial sums into set 0
-                torch.maximum(self.radii_max, stats[j][0], out=self.radii_max)
-                self.observe_count += stats[j][1]
-                if j > 0:
-                    self.buckets.flat += self.bucket_sets[j].flat
+            for j in range(1, used):                                # fold the per-stream partial sums into set 0
+                self.buckets.flat += self.bucket_sets[j].flat
             for j in range(used):                                   # later work on the side streams must wait for the fold
                 self.streams[j].wait_stream(main)
             self.buckets.views_accumulated = len(mine)
         if reduce:
             self.buckets.all_reduce()
-            reduce_statistics(self.radii_max, self.observe_count)
+            self.stats.all_reduce()
         return self.buckets.tensors

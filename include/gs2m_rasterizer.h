@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS2M_ABI_VERSION 1
+#define GS2M_ABI_VERSION 2
 
 /* compile-time constants of the path (reference: cuda_rasterizer/config.h:15-18) */
 #define GS2M_NUM_CHANNELS 3
@@ -123,6 +123,13 @@ typedef struct gs2m_backward_args {
     float* dL_dfeatures;        /* [P,10] */
     int accumulate;
     void* stream;
+    /* optional (NULL = off): GS-2M's densification statistics, fused into the per-Gaussian backward so that they see the
+     * gradient of THIS view even in accumulate mode (scene/gaussian_model.py:569-573 add_densification_stats with
+     * update_filter = radii > 0): accum += |dL_dmeans2D.xy|, accum_abs += |dL_dmeans2D.zw|, denom += 1.  float[P] each,
+     * updated atomically (several views may be in flight on different streams). */
+    float* densify_grad_accum;
+    float* densify_grad_accum_abs;
+    float* densify_denom;
 } gs2m_backward_args;
 
 int gs2m_rasterize_backward(const gs2m_backward_args* args);
@@ -200,6 +207,12 @@ int gs2m_postblend_forward(int width, int height, float fx, float fy, float cx, 
 int gs2m_postblend_backward(int width, int height, float fx, float fy, float cx, float cy, int z_depth,
                             const float* world_view_transform, const float* buffer, const float* dL_dlocal_normal_map,
                             const float* dL_ddepth_map, float* dL_dbuffer, void* stream);
+
+/* ---- per-view densification statistics of the forward outputs ----
+ * train.py:225-228: mask = (observe > 0) & (radii > 0); max_radii2D = where(mask, max(max_radii2D, radii), max_radii2D);
+ * train.py:238-241 (multi-view trim): observe_cnt[observe > 0] += 1.  float[P] each (the reference keeps both as float
+ * tensors); either may be NULL; updated atomically. */
+int gs2m_view_stats_update(int P, const int* radii, const int* observe, float* max_radii2D, float* observe_cnt, void* stream);
 
 /* ---- per-stage device timing (bench.py's roofline leg) ----
  * When enabled, forward/backward bracket every stage with cudaEvents on the launching stream.  gs2m_profile_read

@@ -20,13 +20,16 @@ P, W, H, F, N_VIEWS = 40_000, 480, 320, 10, 4
 def _make_render(dgr, scene, cams, feats, gc, gb):
     settings = {v: syn.raster_settings_for(cams[v], F, dgr.GaussianRasterizationSettings) for v in cams}
 
+    holder = {}
+
     def render_view(v, buckets, accumulate):
         color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
                                                                scene.scales, scene.rotations, None, feats[v], settings[v])
         dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], radii,
-                         settings[v], state, grads=buckets.tensors, accumulate=accumulate)
+                         settings[v], state, grads=buckets.tensors, accumulate=accumulate,
+                         densify_stats=holder["step"].stats.backward_args())
         return {"radii": radii, "observe": observe}
-    return render_view
+    return render_view, holder
 
 
 def _setup(device):
@@ -48,13 +51,14 @@ def _worker(rank, world, port, out_dir, n_streams):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     try:
         dgr, scene, cams, feats, gc, gb = _setup(device)
-        step = vp.ViewShardedStep(P, 16, device, _make_render(dgr, scene, cams, feats, gc, gb), n_streams=n_streams)
+        render, holder = _make_render(dgr, scene, cams, feats, gc, gb)
+        step = holder["step"] = vp.ViewShardedStep(P, 16, device, render, n_streams=n_streams)
         for t in step.buckets.tensors.values():
             t.fill_(7.0)                                    # stale content must not leak into the step
         grads = step.run(N_VIEWS)
         torch.cuda.synchronize(device)
-        torch.save({"grads": {k: grads[k].cpu() for k in step.buckets.names}, "radii": step.radii_max.cpu(),
-                    "observe": step.observe_count.cpu()}, os.path.join(out_dir, "rank%d.pt" % rank))
+        torch.save({"grads": {k: grads[k].cpu() for k in step.buckets.names}, "stats": step.stats.flat.cpu()},
+                   os.path.join(out_dir, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
 
@@ -78,7 +82,8 @@ def test_two_gpu_step_equals_single_gpu_sequential_sum(tmp_path, n_streams):
     # single-GPU sequential reference: the same four views, one after the other, on cuda:0
     device = torch.device("cuda", 0)
     dgr, scene, cams, feats, gc, gb = _setup(device)
-    ref_step = vp.ViewShardedStep(P, 16, device, _make_render(dgr, scene, cams, feats, gc, gb), world=1, rank=0)
+    render, holder = _make_render(dgr, scene, cams, feats, gc, gb)
+    ref_step = holder["step"] = vp.ViewShardedStep(P, 16, device, render, world=1, rank=0)
     ref = ref_step.run(N_VIEWS, reduce=False)
     for k in vp.REDUCED:
         for r in range(world):
@@ -86,6 +91,11 @@ def test_two_gpu_step_equals_single_gpu_sequential_sum(tmp_path, n_streams):
             err, _ = helpers.grad_errors(res[r]["grads"][k], ref[k].cpu())
             assert err <= tol, "%s rank %d: %.3e" % (k, r, err)
         assert torch.equal(res[0]["grads"][k], res[1]["grads"][k])      # all ranks hold identical bits
+    ref_stats = ref_step.stats.flat.cpu()
+    assert 0 < float(ref_stats[3 * P:4 * P].max()) <= N_VIEWS                    # denom counts the views that saw a Gaussian
     for r in range(world):
-        assert torch.equal(res[r]["radii"], ref_step.radii_max.cpu())
-        assert torch.equal(res[r]["observe"], ref_step.observe_count.cpu())
+        # max_radii2D, denom and observe_cnt are exact; the two gradient-norm sums differ by summation order only
+        for lo, hi in ((0, P), (3 * P, 5 * P)):
+            assert torch.equal(res[r]["stats"][lo:hi], ref_stats[lo:hi])
+        torch.testing.assert_close(res[r]["stats"][P:3 * P], ref_stats[P:3 * P], rtol=1e-4, atol=1e-9)
+    assert torch.equal(res[0]["stats"], res[1]["stats"])

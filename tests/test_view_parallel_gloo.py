@@ -44,9 +44,10 @@ def _worker(rank, world, port, n_views, P, M, out_dir):
                 else:
                     t.copy_(g)          # first view of the step overwrites (kernels write every element)
             radii = torch.full((P,), v + 1, dtype=torch.int32)
+            radii[(v + 1) % P] = 0                                  # one culled Gaussian per view
             observe = torch.zeros(P, dtype=torch.int32)
             observe[v % P] = 3
-            return {"radii": radii, "observe": observe}
+            return {"radii": radii, "observe": observe, "means2D_grad": _fake_view_gradient(v * 31 + len("dL_dmeans2D"), (P, 4))}
 
         step = vp.ViewShardedStep(P, M, "cpu", render_view)
         assert step.world == world and step.rank == rank
@@ -54,8 +55,10 @@ def _worker(rank, world, port, n_views, P, M, out_dir):
         for t in step.buckets.tensors.values():
             t.fill_(123.0)
         grads = step.run(n_views)
-        torch.save({"grads": {k: grads[k].clone() for k in step.buckets.names}, "radii": step.radii_max.clone(),
-                    "observe": step.observe_count.clone(), "mine": step.local_views(n_views)},
+        torch.save({"grads": {k: grads[k].clone() for k in step.buckets.names}, "radii": step.stats.max_radii2D.clone(),
+                    "observe": step.stats.observe_cnt.clone(), "accum": step.stats.xyz_gradient_accum.clone(),
+                    "accum_abs": step.stats.xyz_gradient_accum_abs.clone(), "denom": step.stats.denom.clone(),
+                    "mine": step.local_views(n_views)},
                    os.path.join(out_dir, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
@@ -83,6 +86,23 @@ def test_two_rank_step_equals_sequential_sum(tmp_path, n_views):
             expect += _fake_view_gradient(v * 31 + len(k), shapes[k])
         for r in range(world):   # every rank holds the batch gradient == single-process sequential sum
             torch.testing.assert_close(res[r]["grads"][k], expect, rtol=1e-6, atol=1e-6)
+    # densification statistics, reference semantics (train.py:225-241, scene/gaussian_model.py:569-573), sequentially
+    max_r, cnt = torch.zeros(P), torch.zeros(P, 1)
+    accum, accum_abs, denom = torch.zeros(P, 1), torch.zeros(P, 1), torch.zeros(P, 1)
+    for v in range(n_views):
+        radii = torch.full((P,), float(v + 1)); radii[(v + 1) % P] = 0
+        observe = torch.zeros(P); observe[v % P] = 3
+        mask = (observe > 0) & (radii > 0)
+        max_r = torch.where(mask, torch.max(max_r, radii), max_r)
+        cnt[observe > 0] += 1
+        g = _fake_view_gradient(v * 31 + len("dL_dmeans2D"), (P, 4))
+        vis = radii > 0
+        accum[vis] += torch.norm(g[vis, :2], dim=-1, keepdim=True)
+        accum_abs[vis] += torch.norm(g[vis, 2:], dim=-1, keepdim=True)
+        denom[vis] += 1
     for r in range(world):
-        assert int(res[r]["radii"].max()) == n_views                    # MAX over views and ranks
-        assert int(res[r]["observe"].sum()) == n_views                   # one hit per view, SUM over ranks
+        assert torch.equal(res[r]["radii"], max_r)                       # MAX over views and ranks
+        assert torch.equal(res[r]["observe"], cnt)                       # SUM over views and ranks
+        assert torch.equal(res[r]["denom"], denom)
+        torch.testing.assert_close(res[r]["accum"], accum, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(res[r]["accum_abs"], accum_abs, rtol=1e-6, atol=1e-6)

@@ -66,3 +66,37 @@ for name, fn in (("torch eager (reference ops)", ref.derive_maps), ("fused CUDA"
         e0.record(); run_maps(fn); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print("%-30s derive_maps %dx%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, W, H, min(ts), sorted(ts)[len(ts) // 2]))
+
+
+# ---- densification statistics: the reference's eager ops vs the fused forward-side kernel ----
+# (the gradient-norm half is fused into the backward kernel: +0.025 ms per view, bench.py stage `preprocess_bwd`)
+import diff_gaussian_rasterization as dgr  # noqa: E402
+import view_parallel as vp  # noqa: E402
+
+st = vp.DensificationStats(P, "cuda")
+radii = torch.randint(0, 30, (P,), device="cuda", dtype=torch.int32)
+observe = torch.randint(0, 3, (P,), device="cuda", dtype=torch.int32)
+g2d = torch.randn(P, 4, device="cuda")
+
+
+def eager_stats():
+    mask = (observe > 0) & (radii > 0)
+    st.max_radii2D.copy_(torch.where(mask, torch.max(st.max_radii2D, radii), st.max_radii2D))
+    st.observe_cnt[observe > 0] += 1
+    st.update_backward_eager(g2d, radii)
+
+
+def fused_stats():
+    dgr.update_view_stats(radii, observe, st.max_radii2D, st.observe_cnt.view(-1))
+
+
+for name, fn in (("torch eager (reference ops, fwd+bwd halves)", eager_stats), ("fused CUDA (forward half)", fused_stats)):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-45s densification stats P=%d  min %.3f ms  median %.3f ms" % (name, P, min(ts), sorted(ts)[len(ts) // 2]))
