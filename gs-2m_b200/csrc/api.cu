@@ -342,6 +342,7 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
         set_error("backward: missing gradient output pointer"); return GS2M_ERR_INVALID_ARGUMENT;
     }
     if (a->R < 0) { set_error("backward: negative R"); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (a->accumulate < 0 || a->accumulate > 2) { set_error("backward: accumulate mode %d outside 0..2", a->accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
     if (a->geometry_bytes < GeomState::carve(nullptr, a->P, nullptr) ||
         a->binning_bytes < BinState::carve(nullptr, a->R, nullptr) ||
         a->image_bytes < ImageState::carve(nullptr, a->width, a->height, nullptr)) {

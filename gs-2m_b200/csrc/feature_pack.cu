@@ -89,9 +89,16 @@ struct PackGrads {
     float *d_xyz, *d_scaling, *d_rotation, *d_opacity, *d_albedo, *d_roughness, *d_metallic;
 };
 
-__global__ void __launch_bounds__(256) pack_backward_kernel(PackIn in, PackGrads g) {
+// ACC: the raw-parameter gradients are updated with += (several views of a data-parallel step, each chained through its own
+// camera); Gaussians the view culled (radii == 0: all upstream gradients are zero) are skipped then.
+template <bool ACC>
+__device__ __forceinline__ void emit(float* p, float v) { if (ACC) *p += v; else *p = v; }
+
+template <bool ACC>
+__global__ void __launch_bounds__(256) pack_backward_kernel(PackIn in, PackGrads g, const int* __restrict__ radii) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= in.P) return;
+    if (ACC && radii != nullptr && radii[i] <= 0) return;
     const Derived d = derive(in, i);
     const float* W = in.wvt;
     float gf[GS2M_NUM_FEATURES];
@@ -143,22 +150,24 @@ __global__ void __launch_bounds__(256) pack_backward_kernel(PackIn in, PackGrads
                    (dqh[2] - d.qh[2] * qd) / d.nqh + gq.z, (dqh[3] - d.qh[3] * qd) / d.nqh + gq.w};
     const float qq = d.q[0] * dq[0] + d.q[1] * dq[1] + d.q[2] * dq[2] + d.q[3] * dq[3];
     const bool clamped = d.nq <= 1e-12f;   // F.normalize divides by the clamped norm: no projection term then
-    *reinterpret_cast<float4*>(g.d_rotation + 4 * (size_t)i) =
-        make_float4((dq[0] - (clamped ? 0.f : d.q[0] * qq)) / d.nq, (dq[1] - (clamped ? 0.f : d.q[1] * qq)) / d.nq,
-                    (dq[2] - (clamped ? 0.f : d.q[2] * qq)) / d.nq, (dq[3] - (clamped ? 0.f : d.q[3] * qq)) / d.nq);
+    float4 dr = make_float4((dq[0] - (clamped ? 0.f : d.q[0] * qq)) / d.nq, (dq[1] - (clamped ? 0.f : d.q[1] * qq)) / d.nq,
+                            (dq[2] - (clamped ? 0.f : d.q[2] * qq)) / d.nq, (dq[3] - (clamped ? 0.f : d.q[3] * qq)) / d.nq);
+    float4* o4 = reinterpret_cast<float4*>(g.d_rotation + 4 * (size_t)i);
+    if (ACC) { const float4 t = *o4; dr.x += t.x; dr.y += t.y; dr.z += t.z; dr.w += t.w; }
+    *o4 = dr;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        g.d_xyz[3 * (size_t)i + k] = dp[k];
-        g.d_scaling[3 * (size_t)i + k] = g.g_scales[3 * (size_t)i + k] * d.s[k];
+        emit<ACC>(g.d_xyz + 3 * (size_t)i + k, dp[k]);
+        emit<ACC>(g.d_scaling + 3 * (size_t)i + k, g.g_scales[3 * (size_t)i + k] * d.s[k]);
         const float a = sigmoidf(in.albedo[3 * (size_t)i + k]);
-        g.d_albedo[3 * (size_t)i + k] = gf[5 + k] * a * (1.0f - a);
+        emit<ACC>(g.d_albedo + 3 * (size_t)i + k, gf[5 + k] * a * (1.0f - a));
     }
     const float o = sigmoidf(in.opacity[i]);
-    g.d_opacity[i] = g.g_opacities[i] * o * (1.0f - o);
+    emit<ACC>(g.d_opacity + i, g.g_opacities[i] * o * (1.0f - o));
     const float ro = sigmoidf(in.roughness[i]);
-    g.d_roughness[i] = gf[8] * ro * (1.0f - ro);
+    emit<ACC>(g.d_roughness + i, gf[8] * ro * (1.0f - ro));
     const float me = sigmoidf(in.metallic[i]);
-    g.d_metallic[i] = in.blend_metallic ? gf[9] * me * (1.0f - me) : 0.0f;
+    emit<ACC>(g.d_metallic + i, in.blend_metallic ? gf[9] * me * (1.0f - me) : 0.0f);
 }
 
 }  // namespace
@@ -186,12 +195,12 @@ int gs2m_pack_forward(int P, const float* xyz, const float* scaling_raw, const f
     return GS2M_OK;
 }
 
-int gs2m_pack_backward(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+static int pack_backward_impl(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
                        const float* albedo_raw, const float* roughness_raw, const float* metallic_raw,
                        const float* world_view_transform, const float* campos, int z_depth, int blend_metallic,
                        const float* dL_dscales, const float* dL_drotations, const float* dL_dopacities, const float* dL_dfeatures,
                        float* d_xyz, float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw,
-                       float* d_roughness_raw, float* d_metallic_raw, void* stream) {
+                       float* d_roughness_raw, float* d_metallic_raw, bool accumulate, const int* radii, void* stream) {
     if (P < 0) { set_error("pack_backward: negative P"); return GS2M_ERR_INVALID_ARGUMENT; }
     if (P == 0) return GS2M_OK;
     if (!xyz || !scaling_raw || !rotation_raw || !opacity_raw || !albedo_raw || !roughness_raw || !metallic_raw ||
@@ -204,9 +213,35 @@ int gs2m_pack_backward(int P, const float* xyz, const float* scaling_raw, const 
     PackGrads g{dL_dscales, dL_drotations, dL_dopacities, dL_dfeatures, d_xyz, d_scaling_raw, d_rotation_raw, d_opacity_raw,
                 d_albedo_raw, d_roughness_raw, d_metallic_raw};
     count_launches(1);
-    pack_backward_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, g);
+    if (accumulate) pack_backward_kernel<true><<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, g, radii);
+    else pack_backward_kernel<false><<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, g, nullptr);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
+}
+
+int gs2m_pack_backward(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                       const float* albedo_raw, const float* roughness_raw, const float* metallic_raw,
+                       const float* world_view_transform, const float* campos, int z_depth, int blend_metallic,
+                       const float* dL_dscales, const float* dL_drotations, const float* dL_dopacities, const float* dL_dfeatures,
+                       float* d_xyz, float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw,
+                       float* d_roughness_raw, float* d_metallic_raw, void* stream) {
+    return pack_backward_impl(P, xyz, scaling_raw, rotation_raw, opacity_raw, albedo_raw, roughness_raw, metallic_raw,
+                              world_view_transform, campos, z_depth, blend_metallic, dL_dscales, dL_drotations, dL_dopacities,
+                              dL_dfeatures, d_xyz, d_scaling_raw, d_rotation_raw, d_opacity_raw, d_albedo_raw, d_roughness_raw,
+                              d_metallic_raw, false, nullptr, stream);
+}
+
+int gs2m_pack_backward_accumulate(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw,
+                                  const float* opacity_raw, const float* albedo_raw, const float* roughness_raw,
+                                  const float* metallic_raw, const float* world_view_transform, const float* campos, int z_depth,
+                                  int blend_metallic, const float* dL_dscales, const float* dL_drotations,
+                                  const float* dL_dopacities, const float* dL_dfeatures, float* d_xyz, float* d_scaling_raw,
+                                  float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw, float* d_roughness_raw,
+                                  float* d_metallic_raw, const int* radii, void* stream) {
+    return pack_backward_impl(P, xyz, scaling_raw, rotation_raw, opacity_raw, albedo_raw, roughness_raw, metallic_raw,
+                              world_view_transform, campos, z_depth, blend_metallic, dL_dscales, dL_drotations, dL_dopacities,
+                              dL_dfeatures, d_xyz, d_scaling_raw, d_rotation_raw, d_opacity_raw, d_albedo_raw, d_roughness_raw,
+                              d_metallic_raw, true, radii, stream);
 }
 
 }  // extern "C"

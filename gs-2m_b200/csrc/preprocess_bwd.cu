@@ -53,8 +53,25 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
         for (int k = 0; k < GS2M_ACC_STRIDE; ++k) acc[k] = 0.f;
     }
 
-    // a culled Gaussian contributes exactly zero: in accumulate mode (+=) there is nothing to do for it at all
-    if (!visible && IO::kAccumulate) return;
+    // a culled Gaussian contributes exactly zero: tensors that are accumulated (+=) need nothing for it, tensors that are
+    // overwritten get zeros
+    if (!visible) {
+        if (!IO::kAccOther) {
+            io.mean2d(make_float4(0.f, 0.f, 0.f, 0.f));
+            io.conic(make_float4(0.f, 0.f, 0.f, 0.f));
+            io.opacity(0.f);
+            for (int k = 0; k < 3; ++k) io.color(k, 0.f);
+            for (int k = 0; k < GS2M_NUM_FEATURES; ++k) io.feature(k, 0.f);
+            for (int k = 0; k < 6; ++k) io.cov(k, 0.f);
+            for (int k = 0; k < 3; ++k) io.scale(k, 0.f);
+            io.rot(make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (!IO::kAccParams) {
+            for (int k = 0; k < 3; ++k) io.mean3d(k, 0.f);
+            for (int k = 0; k < 3 * M; ++k) io.sh_out(k, 0.f);
+        }
+        return;
+    }
 
     // ---- pass-through gradients ----
     io.mean2d(make_float4(acc[0], acc[1], acc[2], acc[3]));
@@ -68,15 +85,6 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
     io.color(0, acc[8]); io.color(1, acc[9]); io.color(2, acc[10]);
 #pragma unroll
     for (int k = 0; k < GS2M_NUM_FEATURES; ++k) io.feature(k, (k < p.F) ? acc[11 + k] : 0.f);
-
-    if (!visible) {
-        for (int k = 0; k < 3; ++k) io.mean3d(k, 0.f);
-        for (int k = 0; k < 6; ++k) io.cov(k, 0.f);
-        for (int k = 0; k < 3; ++k) io.scale(k, 0.f);
-        io.rot(make_float4(0.f, 0.f, 0.f, 0.f));
-        for (int k = 0; k < 3 * M; ++k) io.sh_out(k, 0.f);
-        return;
-    }
 
     const float* __restrict__ vm = p.viewmatrix;
     const float* __restrict__ pm = p.projmatrix;
@@ -298,31 +306,41 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 }
 
 
+// Accumulate modes (gs2m_backward_args::accumulate): 0 = every tensor is overwritten; 1 = every caller-visible tensor is
+// updated with +=; 2 = only the gradients of GS-2M's view-independent raw parameters (dL_dmeans3D, dL_dsh) are updated with
+// +=, the view-dependent rest is overwritten (its chain rule through the caller's packing stage has to run per view).
+template <int MODE>
+struct AccPolicy {
+    static constexpr bool kAccParams = MODE != 0;   // dL_dmeans3D, dL_dsh
+    static constexpr bool kAccOther = MODE == 1;    // dL_dmeans2D, dL_dopacity, dL_dcolor, dL_dfeatures, dL_dcov3D, dL_dscale, dL_drot
+};
+
 // ---- sink 1: straight to global memory (any M) ----
-template <bool ACC>
-struct GlobalIO {
-    static constexpr bool kAccumulate = ACC;
+template <int MODE>
+struct GlobalIO : AccPolicy<MODE> {
+    using AccPolicy<MODE>::kAccParams;
+    using AccPolicy<MODE>::kAccOther;
     const BwdParams& p; size_t i;
     __device__ GlobalIO(const BwdParams& p_, size_t i_) : p(p_), i(i_) {}
     __device__ void mean2d(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
-        if (ACC) { float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        if (kAccOther) { float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
         *o = v;
     }
     __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
-    __device__ void opacity(float v) { put<ACC>(p.dL_dopacity + i, v); }
-    __device__ void color(int k, float v) { put<ACC>(p.dL_dcolor + 3 * i + k, v); }
-    __device__ void feature(int k, float v) { put<ACC>(p.dL_dfeatures + GS2M_NUM_FEATURES * i + k, v); }
-    __device__ void mean3d(int k, float v) { put<ACC>(p.dL_dmeans3D + 3 * i + k, v); }
-    __device__ void cov(int k, float v) { put<ACC>(p.dL_dcov3D + 6 * i + k, v); }
-    __device__ void scale(int k, float v) { put<ACC>(p.dL_dscale + 3 * i + k, v); }
+    __device__ void opacity(float v) { put<kAccOther>(p.dL_dopacity + i, v); }
+    __device__ void color(int k, float v) { put<kAccOther>(p.dL_dcolor + 3 * i + k, v); }
+    __device__ void feature(int k, float v) { put<kAccOther>(p.dL_dfeatures + GS2M_NUM_FEATURES * i + k, v); }
+    __device__ void mean3d(int k, float v) { put<kAccParams>(p.dL_dmeans3D + 3 * i + k, v); }
+    __device__ void cov(int k, float v) { put<kAccOther>(p.dL_dcov3D + 6 * i + k, v); }
+    __device__ void scale(int k, float v) { put<kAccOther>(p.dL_dscale + 3 * i + k, v); }
     __device__ void rot(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
-        if (ACC) { float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        if (kAccOther) { float4 t = *o; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
         *o = v;
     }
     __device__ float sh_in(int k) const { return __ldg(p.shs + 3 * (size_t)p.M * i + k); }
-    __device__ void sh_out(int k, float v) { if (p.dL_dsh) put<ACC>(p.dL_dsh + 3 * (size_t)p.M * i + k, v); }
+    __device__ void sh_out(int k, float v) { if (p.dL_dsh) put<kAccParams>(p.dL_dsh + 3 * (size_t)p.M * i + k, v); }
 };
 
 // ---- sink 2: rows of a shared staging area (M <= 16); the block copies them out coalesced ----
@@ -337,18 +355,18 @@ struct StageSmem {
     float color[256 * ST_V3];
     unsigned char vis[256];         // row visibility: accumulate mode skips the rows of culled Gaussians
 };
-template <bool ACC>
-struct StagedIO {
-    static constexpr bool kAccumulate = ACC;
+template <int MODE>
+struct StagedIO : AccPolicy<MODE> {
+    using AccPolicy<MODE>::kAccOther;
     const BwdParams& p; size_t i; StageSmem& sm; int t; int sh_row;
     __device__ StagedIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
     __device__ void mean2d(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
-        if (ACC) red_add_f4(o, v);
+        if (kAccOther) red_add_f4(o, v);
         else *o = v;
     }
     __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
-    __device__ void opacity(float v) { if (ACC) atomicAdd(p.dL_dopacity + i, v); else p.dL_dopacity[i] = v; }
+    __device__ void opacity(float v) { if (kAccOther) atomicAdd(p.dL_dopacity + i, v); else p.dL_dopacity[i] = v; }
     __device__ void color(int k, float v) { sm.color[t * ST_V3 + k] = v; }
     __device__ void feature(int k, float v) { sm.feat[t * ST_FEAT + k] = v; }
     __device__ void mean3d(int k, float v) { sm.mean3d[t * ST_V3 + k] = v; }
@@ -356,7 +374,7 @@ struct StagedIO {
     __device__ void scale(int k, float v) { sm.scale[t * ST_V3 + k] = v; }
     __device__ void rot(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
-        if (ACC) red_add_f4(o, v);
+        if (kAccOther) red_add_f4(o, v);
         else *o = v;
     }
     __device__ float sh_in(int k) const { return sm.sh[t * sh_row + k]; }
@@ -390,16 +408,17 @@ __device__ __forceinline__ void block_store(float* __restrict__ dst, const float
     }
 }
 
-template <bool ACC>
+template <int MODE>
 __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdParams p, GeomState g) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
-    GlobalIO<ACC> io(p, (size_t)idx);
+    GlobalIO<MODE> io(p, (size_t)idx);
     gaussian_backward(p, g, idx, p.radii[idx] > 0, io);
 }
 
-template <bool ACC>
+template <int MODE>
 __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
+    constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StageSmem& sm = *reinterpret_cast<StageSmem*>(smem_raw);
     const int t = threadIdx.x;
@@ -433,7 +452,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
     }
     sm.vis[t] = visible ? 1 : 0;
     if (inside) {
-        StagedIO<ACC> io(p, (size_t)idx, sm, t);
+        StagedIO<MODE> io(p, (size_t)idx, sm, t);
         gaussian_backward(p, g, idx, visible, io);
     }
     __syncthreads();
@@ -443,27 +462,27 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         if ((sh_row & 3) == 0) {
             for (int e4 = t; e4 < (n >> 2); e4 += 256) {
                 const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
-                if (ACC && !sm.vis[r]) continue;
+                if (kAccParams && !sm.vis[r]) continue;
                 const float* q = sm.sh + r * sh_pad + c;
                 float4 v = make_float4(q[0], q[1], q[2], q[3]);
                 float4* d4 = reinterpret_cast<float4*>(dst) + e4;
-                if (ACC) red_add_f4(d4, v);
+                if (kAccParams) red_add_f4(d4, v);
                 else *d4 = v;
             }
         } else {
             for (int e = t; e < n; e += 256) {
                 const int r = e / sh_row, c = e - r * sh_row;
-                if (ACC && !sm.vis[r]) continue;
+                if (kAccParams && !sm.vis[r]) continue;
                 const float v = sm.sh[r * sh_pad + c];
-                dst[e] = ACC ? dst[e] + v : v;
+                dst[e] = kAccParams ? dst[e] + v : v;
             }
         }
     }
-    block_store<ACC, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
-    block_store<ACC, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
-    block_store<ACC, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
-    block_store<ACC, ST_V3>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
-    block_store<ACC, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
+    block_store<kAccOther, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
+    block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
+    block_store<kAccParams, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
+    block_store<kAccOther, ST_V3>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
+    block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
 }
 
 }  // namespace
@@ -472,18 +491,22 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
     if (p.P == 0) return GS2M_OK;
     const int blocks = (p.P + 255) / 256;
     count_launches(1);
+    if (p.accumulate < 0 || p.accumulate > 2) { set_error("accumulate mode %d outside 0..2", p.accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
     if (p.M <= 16) {
         static std::atomic<bool> configured{false};
         if (!configured) {
-            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
-            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
+            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
+            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
+            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
             configured = true;
         }
-        if (p.accumulate) preprocess_backward_staged_kernel<true><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
-        else preprocess_backward_staged_kernel<false><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
+        if (p.accumulate == 1) preprocess_backward_staged_kernel<1><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
+        else if (p.accumulate == 2) preprocess_backward_staged_kernel<2><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
+        else preprocess_backward_staged_kernel<0><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
     } else {
-        if (p.accumulate) preprocess_backward_generic_kernel<true><<<blocks, 256, 0, s>>>(p, g);
-        else preprocess_backward_generic_kernel<false><<<blocks, 256, 0, s>>>(p, g);
+        if (p.accumulate == 1) preprocess_backward_generic_kernel<1><<<blocks, 256, 0, s>>>(p, g);
+        else if (p.accumulate == 2) preprocess_backward_generic_kernel<2><<<blocks, 256, 0, s>>>(p, g);
+        else preprocess_backward_generic_kernel<0><<<blocks, 256, 0, s>>>(p, g);
     }
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;

@@ -171,7 +171,8 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
                  radii, raster_settings: GaussianRasterizationSettings, state: RasterState, grads=None,
                  accumulate=False, densify_stats=None):
     """Run the backward pipeline into ``grads`` (dict from :func:`alloc_grads`; allocated when None).
-    With ``accumulate=True`` the nine caller-visible tensors are updated with ``+=``.
+    With ``accumulate=True`` (or 1) the nine caller-visible tensors are updated with ``+=``; with ``accumulate=2`` only
+    ``dL_dmeans3D`` and ``dL_dsh`` (GS-2M's raw, view-independent parameters) are, the rest is overwritten.
     ``densify_stats = (xyz_gradient_accum, xyz_gradient_accum_abs, denom)`` (float ``[P]`` / ``[P,1]`` CUDA tensors, any may be
     None) are updated like ``GaussianModel.add_densification_stats`` with this view's screen-space gradient."""
     lib = _native.load()
@@ -223,7 +224,7 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
         for name, _c in _GRAD_SHAPES:
             setattr(b, name, _ptr(grads[name]))
         b.dL_dsh = _ptr(grads["dL_dsh"]) if M > 0 else None
-        b.accumulate = int(bool(accumulate))
+        b.accumulate = int(accumulate)
         b.stream = torch.cuda.current_stream(dev).cuda_stream
         if densify_stats is not None:
             for t in densify_stats:

@@ -83,6 +83,7 @@ EXPORTS = [
     ("gs2m_inclusive_sum_u32", C.c_int, [_fp, _fp, C.c_int, _fp, C.c_void_p]),
     ("gs2m_pack_forward", C.c_int, [C.c_int] + [_fp] * 9 + [C.c_int, C.c_int] + [_fp] * 4 + [C.c_void_p]),
     ("gs2m_pack_backward", C.c_int, [C.c_int] + [_fp] * 9 + [C.c_int, C.c_int] + [_fp] * 11 + [C.c_void_p]),
+    ("gs2m_pack_backward_accumulate", C.c_int, [C.c_int] + [_fp] * 9 + [C.c_int, C.c_int] + [_fp] * 12 + [C.c_void_p]),
     ("gs2m_postblend_forward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
     ("gs2m_postblend_backward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
     ("gs2m_view_stats_update", C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]),

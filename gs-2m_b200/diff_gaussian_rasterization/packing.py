@@ -73,6 +73,31 @@ def activate_and_pack(xyz, scaling, rotation, opacity, albedo, roughness, metall
                                   camera_center, z_depth, blend_metallic)
 
 
+def pack_backward_accumulate(xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform, camera_center,
+                             g_scales, g_rotations, g_opacities, g_features, d_xyz, d_scaling, d_rotation, d_opacity, d_albedo,
+                             d_roughness, d_metallic, radii=None, z_depth=False, blend_metallic=False):
+    """Packing-stage backward of one view with ``+=`` into the seven raw-parameter gradient tensors (C-ABI
+    ``gs2m_pack_backward_accumulate``); with ``radii`` (int32 ``[P]`` of that view's forward) culled Gaussians are skipped."""
+    lib = _native.load()
+    if not xyz.is_cuda:
+        raise RuntimeError("pack_backward_accumulate has no CPU path: inputs must be CUDA tensors")
+    dev, P = xyz.device, int(xyz.shape[0])
+    ts = [_f32(t, dev, "tensor %d" % k) for k, t in enumerate(
+        (xyz, scaling, rotation, opacity, albedo, roughness, metallic, world_view_transform, camera_center,
+         g_scales, g_rotations, g_opacities, g_features))]
+    outs = (d_xyz, d_scaling, d_rotation, d_opacity, d_albedo, d_roughness, d_metallic)
+    for t, c in zip(outs, (3, 3, 4, 1, 3, 1, 1)):
+        if t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * c:
+            raise RuntimeError("pack_backward_accumulate: gradient outputs must be contiguous float32 [P,%d] on %s" % (c, dev))
+    if radii is not None and (radii.dtype != torch.int32 or radii.numel() != P or not radii.is_contiguous()):
+        raise RuntimeError("pack_backward_accumulate: radii must be a contiguous int32 [P] tensor")
+    with torch.cuda.device(dev):
+        _native.check(lib.gs2m_pack_backward_accumulate(
+            P, *[t.data_ptr() for t in ts[:9]], int(bool(z_depth)), int(bool(blend_metallic)), *[t.data_ptr() for t in ts[9:]],
+            *[t.data_ptr() for t in outs], None if radii is None else radii.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream), "gs2m_pack_backward_accumulate")
+
+
 class _DeriveMaps(torch.autograd.Function):
     @staticmethod
     def forward(ctx, buffer, wvt, fx, fy, cx, cy, z_depth):

@@ -88,6 +88,76 @@ class GradientBuckets:
         return [work] if async_op else []
 
 
+class ParameterBuckets:
+    """Gradients of GS-2M's nine trained parameter groups (64 floats per Gaussian at M = 16) as views of
+    one flat buffer: ``xyz (P,3)``, ``sh (P,M,3)`` (``_features_dc`` and ``_features_rest`` side by side, as ``get_features``
+    concatenates them), ``scaling (P,3)``, ``rotation (P,4)``, ``opacity (P,1)``, ``albedo (P,3)``, ``roughness (P,1)``,
+    ``metallic (P,1)`` — all w.r.t. the RAW (pre-activation) tensors.
+
+    ``features``, the normals inside it and the activated scale / rotation / opacity reach the rasterizer through the
+    camera-dependent packing stage (gaussian_renderer/__init__.py:49-96), so their gradients cannot be summed over views
+    before the chain rule: every view runs  rasterizer backward (``accumulate=2``: ``dL_dmeans3D`` and ``dL_dsh`` add straight
+    into ``xyz`` / ``sh``, the view-dependent rest is overwritten in the per-view scratch)  ->  ``chain_view`` (fused packing
+    backward with ``+=`` into the other six groups and ``xyz``).  One SUM all-reduce over the flat buffer ends the step.
+    """
+
+    names = ("xyz", "sh", "scaling", "rotation", "opacity", "albedo", "roughness", "metallic")
+
+    def __init__(self, P: int, M: int, device, names: Sequence[str] = ()):
+        shapes = {"xyz": (P, 3), "sh": (P, M, 3), "scaling": (P, 3), "rotation": (P, 4), "opacity": (P, 1), "albedo": (P, 3),
+                  "roughness": (P, 1), "metallic": (P, 1)}
+        offsets, total = {}, 0
+        for n in self.names:
+            offsets[n] = total
+            numel = 1
+            for d in shapes[n]:
+                numel *= d
+            total += (numel + 31) // 32 * 32                     # 128-byte granularity
+            shapes[n] = (shapes[n], numel)
+        self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
+        self.tensors: Dict[str, torch.Tensor] = {
+            n: self.flat[offsets[n]:offsets[n] + shapes[n][1]].view(shapes[n][0]) for n in self.names}
+        self._packed_from = offsets["scaling"]                   # everything behind xyz and sh comes from chain_view
+        # per-view scratch: the rasterizer-side gradients that are consumed by chain_view (or unused by GS-2M)
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)  # noqa: E731
+        self.raster = {"dL_dmeans3D": self.tensors["xyz"], "dL_dsh": self.tensors["sh"], "dL_dmeans2D": z(P, 4),
+                       "dL_dconic": z(P, 4), "dL_dopacity": z(P, 1), "dL_dcolor": z(P, 3), "dL_dcov3D": z(P, 6),
+                       "dL_dscale": z(P, 3), "dL_drot": z(P, 4), "dL_dfeatures": z(P, 10)}
+        self.views_accumulated = 0
+
+    def zero_(self):
+        self.flat.zero_()
+        self.views_accumulated = 0
+
+    def nbytes_reduced(self) -> int:
+        return sum(self.tensors[n].numel() * 4 for n in self.names)
+
+    def raster_accumulate_mode(self, accumulate: bool) -> int:
+        """``accumulate`` argument of ``backward_raw`` for this view; the first view of a step overwrites ``xyz`` / ``sh``
+        (the kernel writes every element) and clears the groups ``chain_view`` adds into."""
+        if not accumulate:
+            self.flat[self._packed_from:].zero_()
+            return 0
+        return 2
+
+    def chain_view(self, raw: Dict[str, torch.Tensor], world_view_transform, camera_center, radii, z_depth=False,
+                   blend_metallic=False):
+        """Packing-stage chain rule of one view, ``+=`` into the raw-parameter gradients (Gaussians the view culled are skipped)."""
+        from diff_gaussian_rasterization import packing
+        t, r = self.tensors, self.raster
+        packing.pack_backward_accumulate(
+            raw["xyz"], raw["scaling"], raw["rotation"], raw["opacity"], raw["albedo"], raw["roughness"], raw["metallic"],
+            world_view_transform, camera_center, r["dL_dscale"], r["dL_drot"], r["dL_dopacity"], r["dL_dfeatures"],
+            t["xyz"], t["scaling"], t["rotation"], t["opacity"], t["albedo"], t["roughness"], t["metallic"], radii,
+            z_depth=z_depth, blend_metallic=blend_metallic)
+
+    def all_reduce(self, async_op: bool = False):
+        if not _dist_ready():
+            return []
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return [work] if async_op else []
+
+
 class DensificationStats:
     """GS-2M's densification bookkeeping for one step, reference semantics and dtypes (float tensors):
 
@@ -158,13 +228,14 @@ class ViewShardedStep:
     """
 
     def __init__(self, P: int, M: int, device, render_view: Callable[[int, GradientBuckets, bool], Optional[dict]],
-                 world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1):
+                 world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1, buckets_cls=None):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
         self.device = torch.device(device)
         use_streams = n_streams > 1 and self.device.type == "cuda"
         self.n_streams = n_streams if use_streams else 1
-        self.bucket_sets = [GradientBuckets(P, M, device) for _ in range(self.n_streams)]
+        buckets_cls = buckets_cls or GradientBuckets        # ParameterBuckets: raw-parameter gradients, chained per view
+        self.bucket_sets = [buckets_cls(P, M, device) for _ in range(self.n_streams)]
         self.buckets = self.bucket_sets[0]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)] if use_streams else [None]
         self.render_view = render_view

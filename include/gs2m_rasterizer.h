@@ -108,9 +108,11 @@ typedef struct gs2m_backward_args {
     int feature_count;
     const float* grad_color;    /* dL/d out_color  [3,H,W] */
     const float* grad_buffer;   /* dL/d out_buffer [10,H,W] (only the first feature_count planes are read) */
-    /* outputs: every element is written (culled Gaussians get zeros) unless `accumulate` is set, in which case the
-     * nine caller-visible gradient tensors are updated with += (view-sharded data parallel step: gradients of
-     * several views are summed in place before one all-reduce). */
+    /* outputs.  accumulate = 0: every element is written (culled Gaussians get zeros).  accumulate = 1: the nine
+     * caller-visible gradient tensors are updated with += (view-sharded data parallel step: gradients of several views
+     * are summed in place before one all-reduce).  accumulate = 2: only dL_dmeans3D and dL_dsh — gradients of GS-2M's raw,
+     * view-independent parameters — are updated with +=; the others are overwritten, because they chain through the
+     * caller's view-dependent packing stage (gs2m_pack_backward_accumulate) once per view. */
     float* dL_dmeans2D;         /* [P,4]  (.xy signed, .zw sum of |.|)  rasterize_points.cu:151 */
     float* dL_dconic;           /* [P,4]  scratch-like output (x,y,-,w) rasterize_points.cu:154 */
     float* dL_dopacity;         /* [P,1] */
@@ -195,6 +197,17 @@ int gs2m_pack_backward(int P, const float* xyz, const float* scaling_raw, const 
                        const float* dL_dscales, const float* dL_drotations, const float* dL_dopacities, const float* dL_dfeatures,
                        float* d_xyz, float* d_scaling_raw, float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw,
                        float* d_roughness_raw, float* d_metallic_raw, void* stream);
+
+/* Same, but the seven raw-parameter gradients are updated with += (the view-sharded step chains every view through its own
+ * camera and sums raw-parameter gradients); `radii` (optional, as returned by the forward) lets the
+ * kernel skip the Gaussians the view culled, whose upstream gradients are all zero. */
+int gs2m_pack_backward_accumulate(int P, const float* xyz, const float* scaling_raw, const float* rotation_raw,
+                                  const float* opacity_raw, const float* albedo_raw, const float* roughness_raw,
+                                  const float* metallic_raw, const float* world_view_transform, const float* campos, int z_depth,
+                                  int blend_metallic, const float* dL_dscales, const float* dL_drotations,
+                                  const float* dL_dopacities, const float* dL_dfeatures, float* d_xyz, float* d_scaling_raw,
+                                  float* d_rotation_raw, float* d_opacity_raw, float* d_albedo_raw, float* d_roughness_raw,
+                                  float* d_metallic_raw, const int* radii, void* stream);
 
 /* ---- caller-side stage behind the rasterizer ----
  * Per-pixel maps GS-2M derives from the blended buffer with ~10 PyTorch kernels (gaussian_renderer/__init__.py:125-141,

@@ -1,0 +1,97 @@
+"""Raw-parameter data-parallel step (the collective runs over GS-2M's nine parameter-gradient tensors):
+per-view chain  rasterizer backward (accumulate mode 2) -> fused packing backward (+=)  against autograd through
+activate_and_pack + the drop-in rasterizer summed over the same views."""
+import pytest
+import torch
+
+import helpers
+import synthetic_scenes as syn
+import view_parallel as vp
+
+pytestmark = pytest.mark.gpu
+
+
+def _raw_parameters(scene):
+    eps = 1e-6
+    logit = lambda p: torch.log(p.clamp(eps, 1 - eps) / (1 - p.clamp(eps, 1 - eps)))  # noqa: E731
+    return {"xyz": scene.means3D.clone(), "scaling": torch.log(scene.scales), "rotation": scene.rotations * 1.7,
+            "opacity": logit(scene.opacities), "albedo": logit(scene.albedo), "roughness": logit(scene.roughness),
+            "metallic": logit(scene.metallic)}
+
+
+@pytest.mark.parametrize("n_streams", [1, 2])
+def test_parameter_step_matches_autograd_over_views(n_streams):
+    import diff_gaussian_rasterization as dgr
+    from diff_gaussian_rasterization.packing import activate_and_pack
+    P, W, H, F, M, n_views = 30_000, 320, 240, 10, 16, 4
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=0.6), "cuda")
+    cams = [syn.camera_to(c, "cuda") for c in syn.make_cameras(n_views, W, H)]
+    settings = [syn.raster_settings_for(c, F, dgr.GaussianRasterizationSettings) for c in cams]
+    gc, gb = (t.cuda() for t in syn.make_upstream_grads(W, H, F))
+    raw = _raw_parameters(scene)
+    order = ("xyz", "scaling", "rotation", "opacity", "albedo", "roughness", "metallic")
+
+    # ---- ground truth: autograd through the packing stage and the drop-in rasterizer, summed over the views ----
+    req = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    sh = scene.shs.clone().requires_grad_(True)
+    total = 0.0
+    for cam, st in zip(cams, settings):
+        s, q, o, f = activate_and_pack(*[req[k] for k in order], cam.world_view_transform, cam.camera_center, blend_metallic=True)
+        means2D = torch.zeros(P, 4, device="cuda", requires_grad=True)
+        color, radii, observe, buffer = dgr.GaussianRasterizer(st)(means3D=req["xyz"], means2D=means2D, opacities=o, shs=sh,
+                                                                    scales=s, rotations=q, features=f)
+        total = total + (color * gc).sum() + (buffer * gb).sum()
+    total.backward()
+    expect = {k: req[k].grad for k in order}
+    expect["sh"] = sh.grad
+
+    # ---- the step: per view  forward -> backward (mode 2) -> chain_view, raw-parameter buckets ----
+    def render_view(v, buckets, accumulate):
+        cam, st = cams[v], settings[v]
+        with torch.no_grad():
+            s, q, o, f = activate_and_pack(*[raw[k] for k in order], cam.world_view_transform, cam.camera_center,
+                                           blend_metallic=True)
+        color, radii, observe, buffer, state = dgr.forward_raw(raw["xyz"], scene.shs, None, o, s, q, None, f, st)
+        dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, s, q, None, f, radii, st, state, grads=buckets.raster,
+                         accumulate=buckets.raster_accumulate_mode(accumulate))
+        buckets.chain_view(raw, cam.world_view_transform, cam.camera_center, radii, blend_metallic=True)
+        return {"radii": radii, "observe": observe}
+
+    step = vp.ViewShardedStep(P, M, "cuda", render_view, world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets)
+    for b in step.bucket_sets:
+        b.flat.fill_(3.0)                                   # stale content must not leak into the step
+    got = step.run(n_views, reduce=False)
+    torch.cuda.synchronize()
+    assert step.buckets.nbytes_reduced() == P * 64 * 4      # 64 floats per Gaussian
+    for k in vp.ParameterBuckets.names:
+        err, l2 = helpers.grad_errors(got[k], expect[k])
+        tol = 2e-3 if k in ("scaling", "rotation") else 1e-4      # the ill-conditioned conic backward feeds these two
+        assert err <= tol and l2 <= tol, "%s: max %.3e l2 %.3e" % (k, err, l2)
+
+
+def test_accumulate_mode_2_overwrites_the_view_dependent_tensors():
+    import diff_gaussian_rasterization as dgr
+    P, W, H, F = 20_000, 256, 192, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    st = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities, scene.scales,
+                                                           scene.rotations, None, feats, st)
+    args = (gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats, radii, st, state)
+    ref = dgr.backward_raw(*args)
+    g = dgr.alloc_grads(P, 16, "cuda")
+    base = {k: 0.37 * float(ref[k].abs().max()) for k in g}   # same magnitude as the gradients (2.0 would swamp them in fp32)
+    for k, t in g.items():
+        t.fill_(base[k])
+    dgr.backward_raw(*args, grads=g, accumulate=2)
+    vis = radii > 0
+    # (two backward runs differ in the last bits: the blend kernel's vector reductions arrive in any order)
+    for k in ("dL_dmeans3D", "dL_dsh"):                      # += for the raw parameters, untouched rows for culled Gaussians
+        err, _ = helpers.grad_errors(g[k][vis] - base[k], ref[k][vis])
+        assert err <= 1e-4, "%s: %.3e" % (k, err)
+        assert bool((g[k][~vis] == torch.tensor(base[k], dtype=torch.float32)).all())
+    for k in ("dL_dmeans2D", "dL_dopacity", "dL_dscale", "dL_drot", "dL_dfeatures", "dL_dcolor", "dL_dcov3D"):
+        err, _ = helpers.grad_errors(g[k], ref[k])          # overwritten ...
+        assert err <= (2e-3 if k in ("dL_dscale", "dL_drot", "dL_dcov3D") else 1e-4), "%s: %.3e" % (k, err)
+        assert float(g[k][~vis].abs().max()) == 0.0, k      # ... with zeros for culled Gaussians
+    with pytest.raises(dgr.RasterizerError):
+        dgr.backward_raw(*args, grads=g, accumulate=3)

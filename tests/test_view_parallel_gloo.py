@@ -30,7 +30,7 @@ def _fake_view_gradient(v, shape):
     return torch.randn(shape, generator=g)
 
 
-def _worker(rank, world, port, n_views, P, M, out_dir):
+def _worker(rank, world, port, n_views, P, M, out_dir, param_buckets=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -49,7 +49,7 @@ def _worker(rank, world, port, n_views, P, M, out_dir):
             observe[v % P] = 3
             return {"radii": radii, "observe": observe, "means2D_grad": _fake_view_gradient(v * 31 + len("dL_dmeans2D"), (P, 4))}
 
-        step = vp.ViewShardedStep(P, M, "cpu", render_view)
+        step = vp.ViewShardedStep(P, M, "cpu", render_view, buckets_cls=vp.ParameterBuckets if param_buckets else None)
         assert step.world == world and step.rank == rank
         # poison the buckets: a stale gradient from a previous step must not leak into this one
         for t in step.buckets.tensors.values():
@@ -72,13 +72,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("n_views", [5, 1])
-def test_two_rank_step_equals_sequential_sum(tmp_path, n_views):
+@pytest.mark.parametrize("n_views,param_buckets", [(5, False), (1, False), (5, True)])
+def test_two_rank_step_equals_sequential_sum(tmp_path, n_views, param_buckets):
     world, P, M = 2, 37, 4
-    mp.spawn(_worker, args=(world, _free_port(), n_views, P, M, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_views, P, M, str(tmp_path), param_buckets), nprocs=world, join=True)
     res = [torch.load(os.path.join(tmp_path, "rank%d.pt" % r)) for r in range(world)]
     assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(n_views))
-    names = vp.REDUCED
+    names = vp.ParameterBuckets.names if param_buckets else vp.REDUCED
     shapes = {k: res[0]["grads"][k].shape for k in names}
     for k in names:
         expect = torch.zeros(shapes[k])
