@@ -245,6 +245,46 @@ def run_ours(args, cfg, rank, world, device):
     e2e_value = n_views * args.steps / (float(ms2[0]) * 1e-3)
     clock_info = clocks.stop() if rank == 0 else None
 
+    # ---- informative third leg: the training-faithful chain of SURVEY.md section 8e.  The features and the activated
+    # scale / rotation / opacity depend on the camera, so every view runs  fused packing forward -> rasterizer forward ->
+    # rasterizer backward (accumulate mode 2) -> fused packing backward (+=)  and the all-reduce covers the 64 floats per
+    # Gaussian of the nine raw parameter groups instead of the 73 of the rasterizer's inputs.  Reported as `param_chain`;
+    # the headline legs above are the north_star path (rasterizer forward+backward on given inputs).
+    from diff_gaussian_rasterization.packing import activate_and_pack
+    raw = syn.raw_parameters(scene)
+    order = ("xyz", "scaling", "rotation", "opacity", "albedo", "roughness", "metallic")
+
+    def render_view_params(v, buckets, accumulate):
+        st, cam = settings[v], cams[v]
+        with torch.no_grad():
+            s_, q_, o_, f_ = activate_and_pack(*[raw[k] for k in order], cam.world_view_transform, cam.camera_center,
+                                               blend_metallic=True)
+        color, radii, observe, buffer, state = dgr.forward_raw(raw["xyz"], scene.shs, None, o_, s_, q_, None, f_, st)
+        dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, s_, q_, None, f_, radii, st, state, grads=buckets.raster,
+                         accumulate=buckets.raster_accumulate_mode(accumulate),
+                         densify_stats=holder["params"].stats.backward_args())
+        buckets.chain_view(raw, cam.world_view_transform, cam.camera_center, radii, blend_metallic=True)
+        return {"radii": radii, "observe": observe}
+
+    step.bucket_sets = step_e2e.bucket_sets = None          # release the 73-float buckets before allocating the 64-float ones
+    step.buckets = step_e2e.buckets = step_prof.buckets = None
+    step_prof.bucket_sets = None
+    step_p = holder["params"] = vp.ViewShardedStep(P, M, device, render_view_params, world=world, rank=rank,
+                                                   n_streams=args.streams, buckets_cls=vp.ParameterBuckets)
+    for _ in range(2):
+        step_p.run(n_views)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_p.run(n_views)
+    e1.record()
+    barrier()
+    ms3 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
+    if world > 1:
+        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+    param_chain_value = n_views * args.steps / (float(ms3[0]) * 1e-3)
+    param_chain_bytes = step_p.buckets.nbytes_reduced()
+
     if rank != 0:
         return None
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
@@ -276,6 +316,9 @@ def run_ours(args, cfg, rank, world, device):
                                 % (ab["total"] / 1e9)},
         "ms_per_view": round(per_view_ms, 4),
         "gpu_launches": int(launches[0]),
+        "param_chain": {"value": round(param_chain_value, 3), "unit": UNIT, "allreduce_bytes": param_chain_bytes,
+                        "what": "per view: fused activation+packing fwd, rasterizer fwd+bwd, fused packing bwd (+=); "
+                                "all-reduce of the 9 raw parameter-gradient groups"},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d * V_per, "d2h_bytes_per_step": d2h * V_per,
                 "wall_ms_per_step": round(wall_ms / args.steps, 4)},
         "roofline": {"bound": "hbm", "kernel": "blend_backward_kernel<%d>" % F, "achieved": round(achieved, 2),

@@ -129,6 +129,19 @@ def rotation_matrices(q):
     return R
 
 
+def raw_parameters(scene: Scene):
+    """The scene as GS-2M's raw (pre-activation) parameter tensors: inverse of the getters of scene/gaussian_model.py:113-172
+    (log scale, un-normalised quaternion, logit opacity / albedo / roughness / metallic)."""
+    eps = 1e-6
+
+    def logit(p):
+        p = p.clamp(eps, 1 - eps)
+        return torch.log(p / (1 - p))
+    return {"xyz": scene.means3D.clone(), "scaling": torch.log(scene.scales), "rotation": scene.rotations * 1.7,
+            "opacity": logit(scene.opacities), "albedo": logit(scene.albedo), "roughness": logit(scene.roughness),
+            "metallic": logit(scene.metallic)}
+
+
 def pack_features(scene: Scene, cam: Camera, feature_count, z_depth=False):
     """The (P,10) side-channel tensor: [1, distance, normal(3), albedo(3), roughness, metallic]
     (gaussian_renderer/__init__.py:82-96). Column 9 is only filled when feature_count is even (blend_metallic)."""

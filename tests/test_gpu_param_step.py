@@ -11,14 +11,6 @@ import view_parallel as vp
 pytestmark = pytest.mark.gpu
 
 
-def _raw_parameters(scene):
-    eps = 1e-6
-    logit = lambda p: torch.log(p.clamp(eps, 1 - eps) / (1 - p.clamp(eps, 1 - eps)))  # noqa: E731
-    return {"xyz": scene.means3D.clone(), "scaling": torch.log(scene.scales), "rotation": scene.rotations * 1.7,
-            "opacity": logit(scene.opacities), "albedo": logit(scene.albedo), "roughness": logit(scene.roughness),
-            "metallic": logit(scene.metallic)}
-
-
 @pytest.mark.parametrize("n_streams", [1, 2])
 def test_parameter_step_matches_autograd_over_views(n_streams):
     import diff_gaussian_rasterization as dgr
@@ -28,7 +20,7 @@ def test_parameter_step_matches_autograd_over_views(n_streams):
     cams = [syn.camera_to(c, "cuda") for c in syn.make_cameras(n_views, W, H)]
     settings = [syn.raster_settings_for(c, F, dgr.GaussianRasterizationSettings) for c in cams]
     gc, gb = (t.cuda() for t in syn.make_upstream_grads(W, H, F))
-    raw = _raw_parameters(scene)
+    raw = syn.raw_parameters(scene)
     order = ("xyz", "scaling", "rotation", "opacity", "albedo", "roughness", "metallic")
 
     # ---- ground truth: autograd through the packing stage and the drop-in rasterizer, summed over the views ----
