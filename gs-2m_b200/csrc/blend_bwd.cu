@@ -3,29 +3,33 @@
 //
 // Behavioural reference: renderCUDA backward (cuda_rasterizer/backward.cu:413-598), which issues 11+F same-address
 // float atomics per (pixel, Gaussian) pair.  This kernel produces the same sums (to fp32 re-association) with
-// *no per-pixel atomics* and *no block-wide barriers in the main loop*:
+// *no per-pixel atomics* and *no block-wide barriers*:
 //
-//   warp-autonomous walk      A CTA is one 16x16 tile, but each of its 8 warps owns an 8x4 pixel block and walks the
-//                             tile's list on its own, 32 entries per step: lane l gathers the 32-byte blend record of
-//                             entry l (the 8 warps of a tile read the same records at about the same time, so these
-//                             hit in L1), proves with the conservative footprint test whether the entry can reach
-//                             the warp's pixel block, and the ballot of those tests is the warp's work list.  Entries
-//                             behind the warp's deepest last-contributor are never touched.  (The round-1 first cut
-//                             staged batches per CTA behind __syncthreads; ncu showed 32% of the stall samples on
-//                             those barriers because the 8 warps of a tile have very unequal work.)
+//   warp-autonomous walk      A tile is 8 warps, each owning an 8x4 pixel block and walking the tile's list on its own,
+//                             32 entries per step (the CTA is only a scheduling unit: two warps per CTA, 96 registers,
+//                             20 warps per SM).  The footprint masks written by the forward say which entries reach the
+//                             warp's block; the ballot of the warp's bit is its work list and only the hit lanes gather
+//                             the 32-byte blend record and stage colour + features in shared memory.  Entries behind
+//                             the warp's deepest last-contributor are never touched.  (The round-1 first cut staged
+//                             batches per CTA behind __syncthreads; ncu showed 32% of the stall samples on those
+//                             barriers because the 8 warps of a tile have very unequal work.)
 //   evaluate (lane = pixel)   For a surviving entry every lane recomputes alpha bit-exactly like the forward, steps
-//                             T <- T/(1-alpha), and needs only two scalars per pair:  w = alpha*T  (weight of the
-//                             colour/feature gradients) and  Q = G * dL/dalpha  (weight of every geometric gradient).
-//                             dL/dalpha uses the scalar recurrence  S <- a_prev*cd_prev + (1-a_prev)*S  with
-//                             cd = <colour+features, dL/dpixel>, algebraically identical to the reference's
-//                             per-channel accum_rec/accum_buf recurrences (backward.cu:546-560).
-//                             (w, Q) of 32 pixels x up to 32 entries are parked in a per-warp shared tile.
-//   reduce (lane = Gaussian)  When 32 entries are parked the warp transposes roles: lane g owns entry g and sums
-//                             over the 32 pixels — 3+F colour/feature sums and 8 geometric moments — privately in
-//                             registers: a shared-memory transpose instead of 21 shuffle butterflies per pair.
-//   accumulate                Lane g adds its 11+F sums to the Gaussian's packed 96-byte accumulator row with
-//                             128-bit vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4): 6 per
-//                             (Gaussian, warp block) instead of 21 x 32 scalar atomics.
+//                             T <- T/(1-alpha) (MUFU.RCP + one Newton step), and needs only two scalars per pair:
+//                             w = alpha*T  (weight of the colour/feature gradients) and  Q = G * dL/dalpha  (weight of
+//                             every geometric gradient).  dL/dalpha uses the scalar recurrence
+//                             S <- a_prev*cd_prev + (1-a_prev)*S  with  cd = <colour+features, dL/dpixel>,
+//                             algebraically identical to the reference's per-channel accum_rec recurrences
+//                             (backward.cu:546-560).  Two entries are evaluated per iteration (independent alpha
+//                             chains).  (w, Q) of 32 pixels x 16 entries are parked in a per-warp shared tile; of the
+//                             entry itself only the Gaussian index is kept (lane e holds entry e's).
+//   reduce (lane = entry x pixel-half)  When 16 entries are parked the warp transposes roles: lane (e, h) owns entry e
+//                             and sums over the 16 pixels of half h — 3+F colour/feature sums, six geometric moments
+//                             and the two AbsGS sums — privately in registers: a shared-memory transpose instead of
+//                             21 shuffle butterflies per pair.  The record is re-gathered here (an L1/L2 hit).
+//   accumulate                The halves are combined with one shuffle per value and lane e adds its 11+F sums to the
+//                             Gaussian's packed 96-byte accumulator row with 128-bit vector reductions
+//                             (red.global.add.v4.f32 -> REDG.E.ADD.F32x4): 6 per (Gaussian, warp block) instead of
+//                             21 x 32 scalar atomics.
 #include <atomic>
 #include "blend_common.cuh"
 

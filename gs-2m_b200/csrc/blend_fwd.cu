@@ -1,15 +1,17 @@
-// Forward blend: one CTA per 16x16 tile walks the tile's depth-sorted Gaussian list front to back and alpha-blends
-// RGB plus the first F feature columns (alpha, distance, normal, albedo, roughness, metallic) into every pixel.
+// Forward blend: every 16x16 tile's depth-sorted Gaussian list is walked front to back and RGB plus the first F feature
+// columns (alpha, distance, normal, albedo, roughness, metallic) are alpha-blended into every pixel.
 //
 // Behavioural reference: renderCUDA (cuda_rasterizer/forward.cu:246-372).  Per pixel the sequence of
 // (power, alpha, test_T, T) values, the termination point, `n_contrib` and the `observe` counts are bit-identical to
 // the reference; what differs is how the work is organised:
-//   * warp-autonomous walk: each of the CTA's 8 warps owns an 8x4 pixel block and walks the tile list on its own,
-//     32 entries per step, with no block-wide barrier anywhere.  Lane l gathers the 32-byte blend record of entry l
-//     with two 128-bit loads (the 8 warps of a tile read the same records at about the same time -> L1 hits), proves
-//     with the conservative footprint test (rect_may_contribute) whether the entry can give any pixel of the block
-//     alpha >= 1/255, and the ballot of those tests is the warp's work list; survivors also stage their colour +
-//     feature vector as 16-byte shared records, instead of the reference's per-pair global re-fetches;
+//   * warp-autonomous walk: a tile is 8 warps, each owning an 8x4 pixel block and walking the tile list on its own,
+//     32 entries per step, with no block-wide barrier anywhere (the CTA is only a scheduling unit: one warp per CTA).
+//     Lane l reads the footprint-mask byte of entry l (footprint_masks.cu: which of the tile's eight warp blocks the
+//     Gaussian can reach with alpha >= 1/255, computed once per instance and shared with the backward); the ballot of
+//     the warp's bit is its work list, and only the hit lanes gather the 32-byte blend record (two 128-bit loads, an
+//     L1/L2 hit for the other warps of the tile) and stage colour + feature vector as 16-byte shared records, instead
+//     of the reference's per-pair global re-fetches.  Indices and masks are fetched two steps ahead, records one;
+//   * two entries are evaluated per iteration with branch-free alpha code; the blend itself stays in list order;
 //   * a warp stops as soon as all of its 32 pixels have terminated (the reference only leaves when all 256 have);
 //   * `observe` increments are aggregated per warp (ballot + popc): one integer reduction per (entry, warp) — sums of
 //     integers, so the totals are exact;
