@@ -142,3 +142,51 @@ def derive_maps(buffer, world_view_transform, fx, fy, cx, cy, z_depth=False):
     """(local_normal_map[3,H,W], depth_map[1,H,W], normal_mask[1,H,W] bool) from the rasterizer's buffer — the fused form of
     gaussian_renderer/__init__.py:125-141 (with scene/cameras.py:71-81 rays); differentiable w.r.t. ``buffer``."""
     return _DeriveMaps.apply(buffer, world_view_transform, fx, fy, cx, cy, z_depth)
+
+
+class _PhotometricLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, render, gt, lambda_ssim):
+        lib = _native.load()
+        if not render.is_cuda:
+            raise RuntimeError("photometric_loss has no CPU path: images must be CUDA tensors")
+        dev = render.device
+        render, gt = _f32(render, dev, "render"), _f32(gt, dev, "gt")
+        if render.dim() != 3 or render.shape != gt.shape:
+            raise RuntimeError("photometric_loss: render and gt must both be (C, H, W)")
+        C_, H, W = (int(d) for d in render.shape)
+        maps = torch.empty((3, C_, H, W), dtype=torch.float32, device=dev)
+        sums = torch.zeros(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_photometric_loss_forward(C_, H, W, render.data_ptr(), gt.data_ptr(), maps[0].data_ptr(),
+                                                            maps[1].data_ptr(), maps[2].data_ptr(), sums.data_ptr(),
+                                                            torch.cuda.current_stream(dev).cuda_stream),
+                          "gs2m_photometric_loss_forward")
+        ctx.save_for_backward(render, gt, maps)
+        ctx.lambda_ssim = float(lambda_ssim)
+        means = sums / float(C_ * H * W)
+        ctx.mark_non_differentiable(means)
+        return (1.0 - ctx.lambda_ssim) * means[0] + ctx.lambda_ssim * (1.0 - means[1]), means
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_means):
+        lib = _native.load()
+        render, gt, maps = ctx.saved_tensors
+        dev = render.device
+        C_, H, W = (int(d) for d in render.shape)
+        grad = torch.empty_like(render)
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_photometric_loss_backward(C_, H, W, render.data_ptr(), gt.data_ptr(), maps[0].data_ptr(),
+                                                             maps[1].data_ptr(), maps[2].data_ptr(), ctx.lambda_ssim,
+                                                             float(g_loss), grad.data_ptr(),
+                                                             torch.cuda.current_stream(dev).cuda_stream),
+                          "gs2m_photometric_loss_backward")
+        return grad, None, None
+
+
+def photometric_loss(render, gt, lambda_ssim=0.2, return_terms=False):
+    """``(1 - lambda) * l1_loss(render, gt) + lambda * (1 - ssim(render, gt))`` on ``(C,H,W)`` images — train.py:102-107 with
+    utils/loss_utils.py:24-70 / the fused-ssim submodule — as one CUDA kernel forward and one backward, differentiable w.r.t.
+    ``render``.  With ``return_terms`` also returns the (detached) ``[mean |render - gt|, mean SSIM]``."""
+    loss, means = _PhotometricLoss.apply(render, gt, lambda_ssim)
+    return (loss, means) if return_terms else loss

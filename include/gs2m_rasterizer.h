@@ -221,6 +221,18 @@ int gs2m_postblend_backward(int width, int height, float fx, float fy, float cx,
                             const float* world_view_transform, const float* buffer, const float* dL_dlocal_normal_map,
                             const float* dL_ddepth_map, float* dL_dbuffer, void* stream);
 
+/* ---- photometric loss on the rendered image and its gradient ----
+ * Lrgb = (1 - lambda) * mean|render - gt| + lambda * (1 - mean SSIM(render, gt))  (train.py:102-107; utils/loss_utils.py:24-25
+ * and :30-70: 11x11 Gaussian window, sigma 1.5, zero "same" padding, per channel, C1 = 0.01^2, C2 = 0.03^2 — what the
+ * fused-ssim submodule computes).  Images are [channels,H,W].  forward: sums[0] += sum|render - gt|, sums[1] += sum SSIM (the
+ * caller zeroes `sums` and forms the means), and the three [channels,H,W] derivative maps the backward needs.  backward:
+ * dL_drender = upstream * dLrgb/drender — directly the `grad_color` of gs2m_rasterize_backward. */
+int gs2m_photometric_loss_forward(int channels, int height, int width, const float* render, const float* gt, float* dm_dE1,
+                                  float* dm_dE11, float* dm_dE12, float* sums, void* stream);
+int gs2m_photometric_loss_backward(int channels, int height, int width, const float* render, const float* gt, const float* dm_dE1,
+                                   const float* dm_dE11, const float* dm_dE12, float lambda_ssim, float upstream,
+                                   float* dL_drender, void* stream);
+
 /* ---- per-view densification statistics of the forward outputs ----
  * train.py:225-228: mask = (observe > 0) & (radii > 0); max_radii2D = where(mask, max(max_radii2D, radii), max_radii2D);
  * train.py:238-241 (multi-view trim): observe_cnt[observe > 0] += 1.  float[P] each (the reference keeps both as float

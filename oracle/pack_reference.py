@@ -69,3 +69,25 @@ def derive_maps(buffer, world_view_transform, fx, fy, cx, cy, z_depth=False):
         denoms = torch.sum(local_normals * rays, dim=-1).view(1, H, W)
         depth_map = buffer[1:2, ...] / -(denoms + 1e-8)
     return local_normal_map, depth_map, normal_mask
+
+
+def photometric_loss(render, gt, lambda_ssim=0.2):
+    """train.py:102-107: (1 - lambda) * l1_loss + lambda * (1 - ssim), with utils/loss_utils.py:24-25 and :30-70 written out
+    (11-tap Gaussian window, sigma 1.5, zero padding 5, one group per channel, C1 = 0.01^2, C2 = 0.03^2)."""
+    import math
+    import torch.nn.functional as F
+    ch = render.shape[0]
+    g = torch.tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)], dtype=torch.float32)
+    g = (g / g.sum()).unsqueeze(1)
+    window = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(ch, 1, 11, 11).contiguous().to(render)
+    img1, img2 = render.unsqueeze(0), gt.unsqueeze(0)
+    mu1 = F.conv2d(img1, window, padding=5, groups=ch)
+    mu2 = F.conv2d(img2, window, padding=5, groups=ch)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = F.conv2d(img1 * img1, window, padding=5, groups=ch) - mu1_sq
+    sigma2_sq = F.conv2d(img2 * img2, window, padding=5, groups=ch) - mu2_sq
+    sigma12 = F.conv2d(img1 * img2, window, padding=5, groups=ch) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    l1 = torch.abs(render - gt).mean()
+    return (1.0 - lambda_ssim) * l1 + lambda_ssim * (1.0 - ssim_map.mean()), l1, ssim_map.mean()

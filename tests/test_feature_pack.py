@@ -105,3 +105,34 @@ def test_cuda_derive_maps_matches_oracle(z_depth):
     ok = ok.expand_as(b)
     err = ((a - b).abs() / (b.abs() + 1e-2 * b.abs().mean()))[ok].max()
     assert err <= 1e-3, "relative error %.3e" % err
+
+
+def test_photometric_loss_oracle_basics():
+    """Identical images: SSIM = 1 and L1 = 0, so the loss vanishes; the oracle runs on the CPU in fp64."""
+    g = torch.Generator().manual_seed(2)
+    img = torch.rand(3, 40, 52, generator=g, dtype=torch.float64)
+    loss, l1, ss = ref.photometric_loss(img, img.clone())
+    assert float(l1) == 0.0 and abs(float(ss) - 1.0) < 1e-12 and abs(float(loss)) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 213, 331), (3, 32, 32), (1, 7, 5), (3, 1090, 1959)])
+def test_cuda_photometric_loss_matches_oracle(shape):
+    """Fused L1 + SSIM loss and its gradient vs the reference's torch ops in fp64."""
+    from diff_gaussian_rasterization.packing import photometric_loss
+    g = torch.Generator().manual_seed(9)
+    render64 = torch.rand(shape, generator=g, dtype=torch.float64)
+    gt64 = (render64 + 0.15 * torch.randn(shape, generator=g, dtype=torch.float64)).clamp(0, 1)
+    render64[:, : shape[1] // 3] = gt64[:, : shape[1] // 3]          # a region of exact agreement: sign(0) = 0 in the L1 term
+    render64.requires_grad_(True)
+    loss64, l1_64, ssim64 = ref.photometric_loss(render64, gt64, 0.2)
+    loss64.backward()
+    render = render64.detach().float().cuda().requires_grad_(True)
+    loss, terms = photometric_loss(render, gt64.float().cuda(), 0.2, return_terms=True)
+    (loss * 1.7).backward()
+    assert abs(float(loss.detach()) - float(loss64.detach())) <= 2e-5 * abs(float(loss64.detach())) + 1e-7
+    assert abs(float(terms[0]) - float(l1_64)) <= 2e-5 * float(l1_64) + 1e-7
+    assert abs(float(terms[1]) - float(ssim64)) <= 2e-5
+    a, b = render.grad.cpu().double() / 1.7, render64.grad
+    err = (a - b).abs().max() / b.abs().max()
+    assert err <= 2e-4, "gradient: %.3e" % err

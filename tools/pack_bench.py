@@ -100,3 +100,28 @@ for name, fn in (("torch eager (reference ops, fwd+bwd halves)", eager_stats), (
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print("%-45s densification stats P=%d  min %.3f ms  median %.3f ms" % (name, P, min(ts), sorted(ts)[len(ts) // 2]))
+
+
+# ---- photometric loss: the reference's torch ops (11x11 grouped conv2d x5) vs the fused kernels ----
+from diff_gaussian_rasterization.packing import photometric_loss  # noqa: E402
+
+render = torch.rand(3, H, W, device="cuda").requires_grad_(True)
+gt_img = torch.rand(3, H, W, device="cuda")
+
+
+def run_loss(fn):
+    out = fn(render, gt_img, 0.2)
+    (out[0] if isinstance(out, tuple) else out).backward()
+    render.grad = None
+
+
+for name, fn in (("torch eager (utils/loss_utils.py ops)", ref.photometric_loss), ("fused CUDA", photometric_loss)):
+    for _ in range(3):
+        run_loss(fn)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run_loss(fn); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-40s L1+SSIM loss %dx%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, W, H, min(ts), sorted(ts)[len(ts) // 2]))
