@@ -60,6 +60,11 @@ class BackwardArgs(C.Structure):
     ]
 
 
+class AdamGroup(C.Structure):
+    _fields_ = [("param", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("grad", _fp), ("rows", C.c_longlong),
+                ("width", C.c_int), ("grad_row_stride", C.c_int), ("grad_col_offset", C.c_int), ("lr", C.c_float)]
+
+
 class StateView(C.Structure):
     _fields_ = [(n, _fp) for n in (
         "depths", "rec_a", "rec_b", "rgb", "cov3D", "clamped", "tiles_touched", "point_offsets", "grad_acc",
@@ -88,6 +93,7 @@ EXPORTS = [
     ("gs2m_postblend_backward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
     ("gs2m_photometric_loss_forward", C.c_int, [C.c_int] * 3 + [_fp] * 6 + [C.c_void_p]),
     ("gs2m_photometric_loss_backward", C.c_int, [C.c_int] * 3 + [_fp] * 5 + [C.c_float, C.c_float, _fp, C.c_void_p]),
+    ("gs2m_adam_step", C.c_int, [C.POINTER(AdamGroup), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     ("gs2m_view_stats_update", C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]),
     ("gs2m_profile_enable", None, [C.c_int]),
     ("gs2m_profile_read", C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -190,3 +190,58 @@ def photometric_loss(render, gt, lambda_ssim=0.2, return_terms=False):
     ``render``.  With ``return_terms`` also returns the (detached) ``[mean |render - gt|, mean SSIM]``."""
     loss, means = _PhotometricLoss.apply(render, gt, lambda_ssim)
     return (loss, means) if return_terms else loss
+
+
+class FusedAdam:
+    """``torch.optim.Adam(groups, lr=0.0, eps=1e-15)`` of ``GaussianModel.training_setup`` (scene/gaussian_model.py:230-242) as ONE
+    kernel launch per step over all parameter groups (C-ABI ``gs2m_adam_step``): default betas, per-group ``lr``, no weight
+    decay, no amsgrad.
+
+    ``groups`` is a list of dicts ``{"name", "param": float32 CUDA tensor (updated in place), "lr"}``.  ``step(grads)`` takes a
+    dict name -> gradient; a gradient may be a *column slice view* of a wider row-major tensor (``buckets.tensors["sh"][:, :1]``
+    for ``f_dc`` and ``[:, 1:]`` for ``f_rest``), which is how the view-sharded step keeps the SH gradient."""
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-15):
+        self.groups = [dict(g) for g in groups]
+        if not 0 < len(self.groups) <= 16:
+            raise RuntimeError("FusedAdam takes 1..16 parameter groups")
+        self.betas, self.eps, self.t = (float(betas[0]), float(betas[1])), float(eps), 0
+        for g in self.groups:
+            p = g["param"]
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("FusedAdam: parameters must be contiguous float32 CUDA tensors (no CPU path)")
+            g["exp_avg"], g["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
+
+    def set_lr(self, name, lr):
+        for g in self.groups:
+            if g["name"] == name:
+                g["lr"] = float(lr)
+
+    def step(self, grads):
+        lib = _native.load()
+        self.t += 1
+        arr = (_native.AdamGroup * len(self.groups))()
+        dev = self.groups[0]["param"].device
+        for k, g in enumerate(self.groups):
+            p, gr = g["param"], grads[g["name"]]
+            rows = int(p.shape[0]) if p.dim() > 0 else 1
+            width = p.numel() // max(rows, 1)
+            if gr.dtype != torch.float32 or gr.device != p.device or gr.numel() != p.numel() or int(gr.shape[0]) != rows:
+                raise RuntimeError("FusedAdam: gradient of %s does not match its parameter" % g["name"])
+            if gr.is_contiguous():
+                stride, off_ptr = width, gr.data_ptr()
+            else:   # a column slice of a wider row-major block: rows keep the parent's stride, the inner part is dense
+                inner = gr.stride()[1:] if gr.dim() > 1 else ()
+                dense, expect = True, 1
+                for d, st in zip(reversed(gr.shape[1:]), reversed(inner)):
+                    dense &= (st == expect) or d == 1
+                    expect *= d
+                if not dense:
+                    raise RuntimeError("FusedAdam: gradient of %s must be contiguous or a column slice of a row-major tensor" % g["name"])
+                stride, off_ptr = int(gr.stride(0)), gr.data_ptr()
+            a = arr[k]
+            a.param, a.exp_avg, a.exp_avg_sq, a.grad = p.data_ptr(), g["exp_avg"].data_ptr(), g["exp_avg_sq"].data_ptr(), off_ptr
+            a.rows, a.width, a.grad_row_stride, a.grad_col_offset, a.lr = rows, width, stride, 0, float(g["lr"])
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_adam_step(arr, len(self.groups), self.t, self.betas[0], self.betas[1], self.eps,
+                                             torch.cuda.current_stream(dev).cuda_stream), "gs2m_adam_step")

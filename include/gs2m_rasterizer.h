@@ -233,6 +233,23 @@ int gs2m_photometric_loss_backward(int channels, int height, int width, const fl
                                    const float* dm_dE11, const float* dm_dE12, float lambda_ssim, float upstream,
                                    float* dL_drender, void* stream);
 
+/* ---- one Adam step over all parameter groups in a single launch ----
+ * torch.optim.Adam(groups, eps=1e-15) of scene/gaussian_model.py:230-242: default betas, per-group learning rate, no weight decay,
+ * no amsgrad.  param / exp_avg / exp_avg_sq are contiguous [rows, width]; the gradient of a group may be a column slice of a wider
+ * row-major matrix (element (r, c) at grad[r * grad_row_stride + grad_col_offset + c]).  `step` counts from 1.  At most 16 groups. */
+typedef struct gs2m_adam_group {
+    float* param;
+    float* exp_avg;
+    float* exp_avg_sq;
+    const float* grad;
+    long long rows;
+    int width;
+    int grad_row_stride;
+    int grad_col_offset;
+    float lr;
+} gs2m_adam_group;
+int gs2m_adam_step(const gs2m_adam_group* groups, int n_groups, int step, double beta1, double beta2, double eps, void* stream);
+
 /* ---- per-view densification statistics of the forward outputs ----
  * train.py:225-228: mask = (observe > 0) & (radii > 0); max_radii2D = where(mask, max(max_radii2D, radii), max_radii2D);
  * train.py:238-241 (multi-view trim): observe_cnt[observe > 0] += 1.  float[P] each (the reference keeps both as float

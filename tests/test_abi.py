@@ -56,6 +56,7 @@ def test_struct_layouts_match_c(lib_path):
     """Compile a tiny C program against the header and compare sizeof/offsetof with the ctypes mirrors."""
     from diff_gaussian_rasterization import _native
     structs = {"gs2m_forward_args": _native.ForwardArgs, "gs2m_backward_args": _native.BackwardArgs,
+               "gs2m_adam_group": _native.AdamGroup,
                "gs2m_state_view": _native.StateView}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gs2m_rasterizer.h"', "int main(void){"]
     for cname, cls in structs.items():

@@ -136,3 +136,37 @@ def test_cuda_photometric_loss_matches_oracle(shape):
     a, b = render.grad.cpu().double() / 1.7, render64.grad
     err = (a - b).abs().max() / b.abs().max()
     assert err <= 2e-4, "gradient: %.3e" % err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [5000, 5001])      # 128-bit state access / element-wise fallback for sizes not divisible by 4
+def test_fused_adam_matches_torch_adam_over_the_nine_groups(P):
+    """One-launch Adam vs torch.optim.Adam(l, lr=0.0, eps=1e-15) with GS-2M's nine groups
+    (scene/gaussian_model.py:230-242); the SH gradient arrives as one (P,16,3) block whose column slices feed f_dc / f_rest."""
+    from diff_gaussian_rasterization.packing import FusedAdam
+    g = torch.Generator().manual_seed(21)
+    shapes = {"xyz": (P, 3), "f_dc": (P, 1, 3), "f_rest": (P, 15, 3), "opacity": (P, 1), "scaling": (P, 3), "rotation": (P, 4),
+              "albedo": (P, 3), "roughness": (P, 1), "metallic": (P, 1)}
+    lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "f_rest": 2.5e-3 / 20, "opacity": 0.05, "scaling": 5e-3, "rotation": 1e-3,
+           "albedo": 0.05, "roughness": 0.05, "metallic": 0.05}
+    init = {k: torch.randn(s, generator=g) for k, s in shapes.items()}
+    ref_params = {k: torch.nn.Parameter(v.clone().cuda()) for k, v in init.items()}
+    opt = torch.optim.Adam([{"params": [ref_params[k]], "lr": lrs[k], "name": k} for k in shapes], lr=0.0, eps=1e-15)
+    ours = {k: v.clone().cuda() for k, v in init.items()}
+    fused = FusedAdam([{"name": k, "param": ours[k], "lr": lrs[k]} for k in shapes])
+    for it in range(4):
+        sh_grad = (torch.randn(P, 16, 3, generator=g) * 10.0 ** (-it)).cuda()
+        grads = {k: (torch.randn(s, generator=g) * 10.0 ** (-2 * it)).cuda() for k, s in shapes.items() if not k.startswith("f_")}
+        grads["f_dc"], grads["f_rest"] = sh_grad[:, :1], sh_grad[:, 1:]          # non-contiguous column slices
+        if it == 2:
+            lrs["xyz"] = 3e-5                                                        # update_learning_rate
+            fused.set_lr("xyz", lrs["xyz"])
+            opt.param_groups[0]["lr"] = lrs["xyz"]
+        for k in shapes:
+            ref_params[k].grad = grads[k].contiguous().clone()
+        opt.step()
+        fused.step(grads)
+    for k in shapes:
+        torch.testing.assert_close(ours[k], ref_params[k].detach(), rtol=2e-6, atol=2e-7, msg=k)
+        torch.testing.assert_close(fused.groups[list(shapes).index(k)]["exp_avg_sq"], opt.state[ref_params[k]]["exp_avg_sq"],
+                                   rtol=1e-6, atol=1e-30)

@@ -125,3 +125,30 @@ for name, fn in (("torch eager (utils/loss_utils.py ops)", ref.photometric_loss)
         e0.record(); run_loss(fn); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print("%-40s L1+SSIM loss %dx%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, W, H, min(ts), sorted(ts)[len(ts) // 2]))
+
+
+# ---- Adam over GS-2M's nine parameter groups: torch.optim.Adam vs the one-launch kernel ----
+from diff_gaussian_rasterization.packing import FusedAdam  # noqa: E402
+
+shapes = {"xyz": (P, 3), "f_dc": (P, 1, 3), "f_rest": (P, 15, 3), "opacity": (P, 1), "scaling": (P, 3), "rotation": (P, 4),
+          "albedo": (P, 3), "roughness": (P, 1), "metallic": (P, 1)}
+params = {k: torch.nn.Parameter(torch.randn(s, device="cuda")) for k, s in shapes.items()}
+sh_grad = torch.randn(P, 16, 3, device="cuda")
+grads = {k: torch.randn(s, device="cuda") for k, s in shapes.items() if not k.startswith("f_")}
+grads["f_dc"], grads["f_rest"] = sh_grad[:, :1], sh_grad[:, 1:]
+for k in shapes:
+    params[k].grad = grads[k].contiguous()
+opt_default = torch.optim.Adam([{"params": [params[k]], "lr": 1e-3} for k in shapes], lr=0.0, eps=1e-15)
+opt_fused = torch.optim.Adam([{"params": [params[k]], "lr": 1e-3} for k in shapes], lr=0.0, eps=1e-15, fused=True)
+ours = FusedAdam([{"name": k, "param": params[k].data, "lr": 1e-3} for k in shapes])
+for name, fn in (("torch.optim.Adam (reference configuration)", opt_default.step), ("torch.optim.Adam(fused=True)", opt_fused.step),
+                 ("gs2m_adam_step (one launch)", lambda: ours.step(grads))):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-45s Adam step P=%d (64 floats/Gaussian)  min %.3f ms  median %.3f ms" % (name, P, min(ts), sorted(ts)[len(ts) // 2]))
