@@ -91,6 +91,8 @@ EXPORTS = [
     ("gs2m_pack_backward_accumulate", C.c_int, [C.c_int] + [_fp] * 9 + [C.c_int, C.c_int] + [_fp] * 12 + [C.c_void_p]),
     ("gs2m_postblend_forward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
     ("gs2m_postblend_backward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int] + [_fp] * 5 + [C.c_void_p]),
+    ("gs2m_sobel_normal_forward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [_fp] * 5 + [C.c_void_p]),
+    ("gs2m_sobel_normal_backward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [_fp] * 7 + [C.c_void_p]),
     ("gs2m_photometric_loss_forward", C.c_int, [C.c_int] * 3 + [_fp] * 6 + [C.c_void_p]),
     ("gs2m_photometric_loss_backward", C.c_int, [C.c_int] * 3 + [_fp] * 5 + [C.c_float, C.c_float, _fp, C.c_void_p]),
     ("gs2m_adam_step", C.c_int, [C.POINTER(AdamGroup), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]),

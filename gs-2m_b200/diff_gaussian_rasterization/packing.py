@@ -144,6 +144,48 @@ def derive_maps(buffer, world_view_transform, fx, fy, cx, cy, z_depth=False):
     return _DeriveMaps.apply(buffer, world_view_transform, fx, fy, cx, cy, z_depth)
 
 
+class _SobelNormal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, alpha, bg, wvt, fx, fy, cx, cy):
+        lib = _native.load()
+        if not depth.is_cuda:
+            raise RuntimeError("sobel_normal_map has no CPU path: depth must be a CUDA tensor")
+        dev = depth.device
+        depth, alpha = _f32(depth, dev, "depth"), _f32(alpha, dev, "alpha")
+        bg, wvt = _f32(bg, dev, "bg_color"), _f32(wvt, dev, "world_view_transform")
+        if depth.dim() != 2 or depth.shape != alpha.shape or bg.numel() != 3:
+            raise RuntimeError("sobel_normal_map: depth and alpha must be (H, W), bg_color (3,)")
+        H, W = int(depth.shape[0]), int(depth.shape[1])
+        out = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        ctx.geom = (W, H, float(fx), float(fy), float(cx), float(cy))
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_sobel_normal_forward(*ctx.geom, wvt.data_ptr(), bg.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                                                        out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                          "gs2m_sobel_normal_forward")
+        ctx.save_for_backward(depth, alpha, bg, wvt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _native.load()
+        depth, alpha, bg, wvt = ctx.saved_tensors
+        dev = depth.device
+        d_depth, d_alpha = torch.empty_like(depth), torch.empty_like(alpha)
+        with torch.cuda.device(dev):
+            _native.check(lib.gs2m_sobel_normal_backward(*ctx.geom, wvt.data_ptr(), bg.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                                                         g_out.contiguous().data_ptr(), d_depth.data_ptr(), d_alpha.data_ptr(),
+                                                         torch.cuda.current_stream(dev).cuda_stream),
+                          "gs2m_sobel_normal_backward")
+        return d_depth, d_alpha, None, None, None, None, None, None
+
+
+def sobel_normal_map(depth_map, alpha_map, bg_color, world_view_transform, fx, fy, cx, cy):
+    """``render_normal_from_depth_map`` (gaussian_renderer/__init__.py:163-175 over utils/normal_utils.py:30-85) as one kernel
+    each way: world-space normals from the ``(H, W)`` depth map, composited over ``bg_color`` with ``alpha_map``; returns
+    ``(3, H, W)``, differentiable w.r.t. depth and alpha."""
+    return _SobelNormal.apply(depth_map, alpha_map, bg_color, world_view_transform, fx, fy, cx, cy)
+
+
 class _PhotometricLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, render, gt, lambda_ssim):

@@ -221,6 +221,16 @@ int gs2m_postblend_backward(int width, int height, float fx, float fy, float cx,
                             const float* world_view_transform, const float* buffer, const float* dL_dlocal_normal_map,
                             const float* dL_ddepth_map, float* dL_dbuffer, void* stream);
 
+/* Normal map from the depth map (the "sobel" normal of the geometry stage; gaussian_renderer/__init__.py:163-175,
+ * utils/normal_utils.py:30-85): back-projection with the pinhole intrinsics, normalize(cross(right - left, top - bottom)) of
+ * the four neighbours in world space, zero on the one-pixel border, composited over `bg` ([3], device) with alpha_map.
+ * depth_map / alpha_map are [H,W], sobel_map is [3,H,W].  The backward returns dL/ddepth_map and dL/dalpha_map. */
+int gs2m_sobel_normal_forward(int width, int height, float fx, float fy, float cx, float cy, const float* world_view_transform,
+                              const float* bg, const float* depth_map, const float* alpha_map, float* sobel_map, void* stream);
+int gs2m_sobel_normal_backward(int width, int height, float fx, float fy, float cx, float cy, const float* world_view_transform,
+                               const float* bg, const float* depth_map, const float* alpha_map, const float* dL_dsobel_map,
+                               float* dL_ddepth_map, float* dL_dalpha_map, void* stream);
+
 /* ---- photometric loss on the rendered image and its gradient ----
  * Lrgb = (1 - lambda) * mean|render - gt| + lambda * (1 - mean SSIM(render, gt))  (train.py:102-107; utils/loss_utils.py:24-25
  * and :30-70: 11x11 Gaussian window, sigma 1.5, zero "same" padding, per channel, C1 = 0.01^2, C2 = 0.03^2 — what the

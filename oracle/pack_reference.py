@@ -91,3 +91,30 @@ def photometric_loss(render, gt, lambda_ssim=0.2):
     ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
     l1 = torch.abs(render - gt).mean()
     return (1.0 - lambda_ssim) * l1 + lambda_ssim * (1.0 - ssim_map.mean()), l1, ssim_map.mean()
+
+
+def sobel_normal_map(depth, alpha, bg_color, world_view_transform, fx, fy, cx, cy):
+    """render_normal_from_depth_map (gaussian_renderer/__init__.py:163-175) with normal_from_depth_image / depth2point /
+    depth_pcd2normal (utils/normal_utils.py:11-85, offset=None, view_space=False) and get_calib_matrix_nerf
+    (scene/cameras.py:83-89) written out with the same torch ops."""
+    H, W = depth.shape
+    intrinsic = torch.tensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=depth.dtype, device=depth.device)
+    extrinsic = world_view_transform.transpose(0, 1).contiguous()
+    valid_x = torch.arange(W, dtype=torch.float32, device=depth.device).to(depth.dtype) / (W - 1)
+    valid_y = torch.arange(H, dtype=torch.float32, device=depth.device).to(depth.dtype) / (H - 1)
+    valid_x, valid_y = torch.meshgrid(valid_x, valid_y, indexing="xy")
+    ndc_xyz = torch.stack([valid_x, valid_y, depth], dim=-1)
+    inv_scale = torch.tensor([[W - 1, H - 1]], dtype=depth.dtype, device=depth.device)
+    cam_z = ndc_xyz[..., 2:3]
+    cam_xy = ndc_xyz[..., :2] * inv_scale * cam_z
+    cam_xyz = torch.cat([cam_xy, cam_z], dim=-1) @ torch.inverse(intrinsic.t())
+    xyz_cam = cam_xyz.reshape(-1, 3)
+    xyz_world = torch.cat([xyz_cam, torch.ones_like(xyz_cam[..., 0:1])], axis=-1) @ torch.inverse(extrinsic).transpose(0, 1)
+    xyz = xyz_world[..., :3].reshape(H, W, 3)
+    bottom_point, top_point = xyz[2:H, 1:W - 1, :], xyz[0:H - 2, 1:W - 1, :]
+    right_point, left_point = xyz[1:H - 1, 2:W, :], xyz[1:H - 1, 0:W - 2, :]
+    xyz_normal = torch.cross(right_point - left_point, top_point - bottom_point, dim=-1)
+    xyz_normal = torch.nn.functional.normalize(xyz_normal, p=2, dim=-1)
+    xyz_normal = torch.nn.functional.pad(xyz_normal.permute(2, 0, 1), (1, 1, 1, 1), mode="constant").permute(1, 2, 0)
+    normal_ref = xyz_normal * alpha[..., None] + bg_color[None, None, ...] * (1.0 - alpha[..., None])
+    return normal_ref.permute(2, 0, 1)

@@ -170,3 +170,29 @@ def test_fused_adam_matches_torch_adam_over_the_nine_groups(P):
         torch.testing.assert_close(ours[k], ref_params[k].detach(), rtol=2e-6, atol=2e-7, msg=k)
         torch.testing.assert_close(fused.groups[list(shapes).index(k)]["exp_avg_sq"], opt.state[ref_params[k]]["exp_avg_sq"],
                                    rtol=1e-6, atol=1e-30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(97, 131), (2, 5), (3, 3)])
+def test_cuda_sobel_normal_matches_oracle(shape):
+    """Normal map from the depth map (the rest of SURVEY.md section 8f rank 2) vs the reference's torch ops in fp64."""
+    from diff_gaussian_rasterization.packing import sobel_normal_map
+    H, W = shape
+    g = torch.Generator().manual_seed(13)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    depth64 = (2.0 + 0.01 * xx + 0.02 * yy + 0.05 * torch.rand(H, W, generator=g, dtype=torch.float64)).requires_grad_(True)
+    alpha64 = torch.rand(H, W, generator=g, dtype=torch.float64).requires_grad_(True)
+    bg64 = torch.tensor([0.2, 0.5, 1.0], dtype=torch.float64)
+    cam = syn.make_cameras(1, max(W, 4), max(H, 4))[0]
+    fx, fy, cx, cy = 1.1 * W, 1.2 * W, 0.5 * W, 0.5 * H
+    ref_out = ref.sobel_normal_map(depth64, alpha64, bg64, cam.world_view_transform.double(), fx, fy, cx, cy)
+    up = torch.randn(3, H, W, generator=g, dtype=torch.float64)
+    ref_out.backward(up)
+    depth = depth64.detach().float().cuda().requires_grad_(True)
+    alpha = alpha64.detach().float().cuda().requires_grad_(True)
+    out = sobel_normal_map(depth, alpha, bg64.float().cuda(), cam.world_view_transform.cuda(), fx, fy, cx, cy)
+    out.backward(up.float().cuda())
+    torch.testing.assert_close(out.detach().cpu().double(), ref_out.detach(), rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(alpha.grad.cpu().double(), alpha64.grad, rtol=2e-4, atol=2e-4)
+    a, b = depth.grad.cpu().double(), depth64.grad
+    assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-6

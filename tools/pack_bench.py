@@ -152,3 +152,29 @@ for name, fn in (("torch.optim.Adam (reference configuration)", opt_default.step
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print("%-45s Adam step P=%d (64 floats/Gaussian)  min %.3f ms  median %.3f ms" % (name, P, min(ts), sorted(ts)[len(ts) // 2]))
+
+
+# ---- normal map from depth (rest of SURVEY.md section 8f rank 2) ----
+from diff_gaussian_rasterization.packing import sobel_normal_map  # noqa: E402
+
+depth_img = (2.0 + torch.rand(H, W, device="cuda")).requires_grad_(True)
+alpha_img = torch.rand(H, W, device="cuda").requires_grad_(True)
+bg3 = torch.zeros(3, device="cuda")
+g_sobel = torch.randn(3, H, W, device="cuda")
+
+
+def run_sobel(fn):
+    fn(depth_img, alpha_img, bg3, cam.world_view_transform, 1.1 * W, 1.1 * W, 0.5 * W, 0.5 * H).backward(g_sobel)
+    depth_img.grad = alpha_img.grad = None
+
+
+for name, fn in (("torch eager (utils/normal_utils.py ops)", ref.sobel_normal_map), ("fused CUDA", sobel_normal_map)):
+    for _ in range(3):
+        run_sobel(fn)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run_sobel(fn); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print("%-40s sobel normal %dx%d fwd+bwd  min %.3f ms  median %.3f ms" % (name, W, H, min(ts), sorted(ts)[len(ts) // 2]))
