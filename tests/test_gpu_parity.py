@@ -83,6 +83,38 @@ def test_forward_and_backward_vs_reference(dgr, ref, P, W, H, F, rad, shell):
         assert l2 <= GRAD_TOL, "%s: relative L2 %.3e" % (k, l2)
 
 
+def _random_cases(n, seed=20261017):
+    """Seeded random (P, W, H, F, camera radius, shell fraction, scene seed, view index): ragged image sizes (tile rows / columns
+    cut anywhere, images smaller than a tile, one-pixel strips), every feature count, cameras from inside the cloud to far away."""
+    import random
+    rng = random.Random(seed)
+    cases = []
+    for k in range(n):
+        P = rng.choice([1, 7, 200, 3_000, 25_000, 60_000])
+        W, H = rng.choice([(1, 1), (5, 300), (300, 5), (17, 33), (251, 190), (640, 361), (1023, 65)])
+        F = rng.randint(0, 10)
+        cases.append(pytest.param(P, W, H, F, rng.choice([0.3, 1.5, 3.0, 8.0]), rng.choice([0.0, 0.6, 1.0]),
+                                  rng.randint(1, 10_000), rng.randint(0, 3), id="rand%02d-P%d-%dx%d-F%d" % (k, P, W, H, F)))
+    return cases
+
+
+@pytest.mark.parametrize("P,W,H,F,rad,shell,scene_seed,view", _random_cases(16))
+def test_random_shapes_vs_reference(dgr, ref, P, W, H, F, rad, shell, scene_seed, view):
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=shell, cam_radius=rad, view=view, n_views=4,
+                                                  scene_seed=scene_seed)
+    if F == 0:
+        gb = torch.zeros_like(gb)
+    r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    assert_forward_bit_exact(o, r, P)
+    for k in GRAD_NAMES:
+        if float(r[k].abs().max()) == 0.0:
+            assert float(o[k].abs().max()) == 0.0, k
+            continue
+        err, l2 = helpers.grad_errors(o[k], r[k])
+        assert err <= (2e-3 if k in ILL_CONDITIONED else 5e-4), "%s: max %.3e l2 %.3e" % (k, err, l2)
+
+
 @pytest.mark.parametrize("F", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 def test_every_feature_count(dgr, ref, F):
     P, W, H = 6000, 200, 136
