@@ -20,20 +20,7 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int tid,
 // Per-pair evaluation, bit-identical to the reference's renderCUDA as compiled for sm_100
 // (cuda_rasterizer/forward.cu:325-339; SASS: dx*a, dy*c, dy*(dy*c), fma(dx, dx*a, .), dy*(dx*b), fma(., -0.5, -.),
 // accurate expf, min(0.99, o*E)).  Returns false when the pair is skipped (power > 0 or alpha < 1/255).
-__device__ __forceinline__ bool pair_alpha(float gx, float gy, float ca, float cb, float cc, float opacity,
-                                           float pxf, float pyf, float& dx, float& dy, float& G, float& alpha) {
-    dx = __fadd_rn(gx, -pxf);
-    dy = __fadd_rn(gy, -pyf);
-    const float s = __fmaf_rn(dx, __fmul_rn(dx, ca), __fmul_rn(dy, __fmul_rn(dy, cc)));
-    const float u = __fmul_rn(dy, __fmul_rn(dx, cb));
-    const float power = __fmaf_rn(s, -0.5f, -u);
-    if (power > 0.0f) return false;
-    G = expf(power);
-    alpha = fminf(__fmul_rn(opacity, G), 0.99f);
-    return !(alpha < 0.00392156885936856f);  // 1.0f / 255.0f
-}
-
-// Branch-free variant (same arithmetic, same decisions): lets two independent evaluations be interleaved.
+// Branch-free (same arithmetic, same decisions as the reference's early-outs): lets two independent evaluations be interleaved.
 __device__ __forceinline__ bool pair_alpha_nb(float gx, float gy, float ca, float cb, float cc, float opacity,
                                               float pxf, float pyf, float& dx, float& dy, float& G, float& alpha) {
     dx = __fadd_rn(gx, -pxf);
@@ -49,7 +36,7 @@ __device__ __forceinline__ bool pair_alpha_nb(float gx, float gy, float ca, floa
 // Lower bound (over an axis-aligned pixel rectangle [x0,x1]x[y0,y1]) of the conic quadratic
 //   q(d) = a dx^2 + 2 b dx dy + c dy^2,   d = pixel - mean,
 // valid when the conic is positive definite.  A pair can only pass the alpha >= 1/255 test where q <= thr
-// (thr = 2 ln(255 opacity), stored by preprocess), so `rect_may_contribute == false` proves that no pixel of the
+// (thr = 2 ln(255 opacity), stored by preprocess), so a lower bound above thr proves that no pixel of the
 // rectangle is blended and the reference's per-pixel tests would all have skipped it.  The margin absorbs the
 // rounding of both this bound and the reference's fp32 power/exp evaluation (scaled by the largest term magnitude
 // that can occur inside the rectangle), so the test only ever errs toward "may contribute".
@@ -68,32 +55,10 @@ __device__ __forceinline__ CullRecord make_cull_record(float4 ra, float4 rb) {
     return r;
 }
 
-__device__ __forceinline__ bool rect_may_contribute(const CullRecord& r, float x0, float y0, float x1, float y1) {
-    if (r.thr < 0.f) return false;          // opacity < 1/255: alpha can never reach 1/255 (exact)
-    if (!r.cullable) return true;
-    const float lx = x0 - r.mx, hx = x1 - r.mx;   // d.x range
-    const float ly = y0 - r.my, hy = y1 - r.my;   // d.y range
-    const bool in_x = (lx <= 0.f) && (hx >= 0.f);
-    const bool in_y = (ly <= 0.f) && (hy >= 0.f);
-    if (in_x && in_y) return true;           // mean inside the rectangle: q = 0 there
-    float qmin = 3.0e38f;
-    if (!in_x) {                             // nearest vertical edge, minimise over d.y in [ly,hy]
-        const float ex = (lx > 0.f) ? lx : hx;
-        const float dy = fminf(fmaxf(-r.b * ex * r.inv_c, ly), hy);
-        qmin = r.a * ex * ex + (2.f * r.b * ex + r.c * dy) * dy;
-    }
-    if (!in_y) {                             // nearest horizontal edge, minimise over d.x in [lx,hx]
-        const float ey = (ly > 0.f) ? ly : hy;
-        const float dx = fminf(fmaxf(-r.b * ey * r.inv_a, lx), hx);
-        qmin = fminf(qmin, r.c * ey * ey + (2.f * r.b * ey + r.a * dx) * dx);
-    }
-    const float ax = fmaxf(fabsf(lx), fabsf(hx)), ay = fmaxf(fabsf(ly), fabsf(hy));
-    const float mag = r.a * ax * ax + r.c * ay * ay + 2.f * fabsf(r.b) * ax * ay;
-    return !(qmin > r.thr + 1e-5f * mag + 1e-3f);
-}
-
-// 8-bit mask: bit w set when warp w's 8x4 pixel block may receive this Gaussian.  Same test as rect_may_contribute for
-// the eight blocks of a tile, with everything that only depends on the block's column (2 of them) or row (4) hoisted.
+// 8-bit mask: bit w set when warp w's 8x4 pixel block may receive this Gaussian.  Per block: thr < 0 (opacity < 1/255) can
+// never contribute (exact); a degenerate conic is never culled; the mean inside the block gives q = 0; otherwise the minimum
+// of q over the rectangle lies on the edge(s) nearest to the mean, where q is a 1-D quadratic minimised in closed form with
+// the minimiser clamped to the edge.  Everything that only depends on the block's column (2 of them) or row (4) is hoisted.
 __device__ __forceinline__ uint32_t warp_block_mask(const CullRecord& r, int tile_px0, int tile_py0) {
     if (r.thr < 0.f) return 0u;
     if (!r.cullable) return 0xFFu;
