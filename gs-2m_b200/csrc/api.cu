@@ -228,7 +228,7 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     //   "depthfirst" (default)  depth-sort the visible Gaussians, emit in depth order, 2-pass sort on the tile id
     //   "sort64"                duplicate + 64-bit onesweep radix sort, the reference's structure
     //   "ranked"                depth-rank + atomic per-tile emission + shared-memory tile sort (binning_v2.cu)
-    // B200, config 4: 0.42 / 0.72 / 0.83 ms (profiles/r1_binning_paths.md); GS2M_BINNING selects the other two.
+    // B200, config 4, binning total: 0.47 / 0.77 / 0.56 ms (profiles/r1_binning_paths.md); GS2M_BINNING selects the other two.
     BinningPath path = binning_path_from_env();
     if (p.P > 0) {
         char* geom_base = a->geometry_buffer(a->geometry_user, GeomState::carve(nullptr, p.P, nullptr));

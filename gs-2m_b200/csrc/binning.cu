@@ -6,10 +6,13 @@
 // All integer work: the outputs are bit-identical to the reference's (stable sort, ties resolved by the emission
 // order = ascending Gaussian index, then row-major tile order).
 //
-// The radix sort is a hand-written single-pass-per-digit ("onesweep") sort: one up-front histogram kernel over all
-// digits, then per 8-bit digit one kernel that ranks a tile of keys with warp match-any, resolves its global base
-// by decoupled look-back over a per-tile status array, and scatters keys+values.  12 B/pair read + 12 B/pair
-// written per digit pass; the work is pure HBM/L2 streaming, the roofline DESIGN.md charges it to.
+// The radix sort is a hand-written single-pass-per-digit ("onesweep") sort, templated on 32- and 64-bit keys: one
+// up-front histogram kernel over all digits, then per 8-bit digit one kernel that ranks a tile of keys with warp
+// match-any, resolves its global base by decoupled look-back over a per-tile status array, stages the tile in sorted
+// order in shared memory and copies it out so that every digit leaves as a coalesced run.  The work is pure HBM/L2
+// streaming, the roofline DESIGN.md charges it to.  The default binning path (binning_depthfirst.cu) uses the 32-bit
+// instance twice (depth bits of the visible Gaussians, then tile ids of the instances); the scan, duplication and
+// 64-bit sort of this file are the reference-shaped "sort64" path and the building blocks the C-ABI exports.
 #include "common.cuh"
 
 namespace gs2m {
