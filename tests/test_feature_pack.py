@@ -172,6 +172,21 @@ def test_fused_adam_matches_torch_adam_over_the_nine_groups(P):
                                    rtol=1e-6, atol=1e-30)
 
 
+def test_sobel_normal_oracle_on_a_fronto_parallel_plane():
+    """A constant depth map is a plane facing the camera: every interior normal is minus the camera's forward axis in world
+    space (a x b = (0, 0, -4 z^2 / (fx fy)) in camera space), the border is background, alpha blends between the two."""
+    H, W = 20, 30
+    cam = syn.make_cameras(1, W, H)[0]
+    wvt = cam.world_view_transform.double()
+    depth = torch.full((H, W), 3.0, dtype=torch.float64)
+    alpha = torch.full((H, W), 0.25, dtype=torch.float64)
+    bg = torch.tensor([0.1, 0.2, 0.3], dtype=torch.float64)
+    out = ref.sobel_normal_map(depth, alpha, bg, wvt, 1.1 * W, 1.3 * W, 0.5 * W, 0.5 * H)
+    expect = -wvt[:3, 2] * 0.25 + bg * 0.75
+    torch.testing.assert_close(out[:, 1:-1, 1:-1], expect[:, None, None].expand(3, H - 2, W - 2), rtol=1e-9, atol=1e-9)
+    torch.testing.assert_close(out[:, 0, :], (bg * 0.75)[:, None].expand(3, W), rtol=0, atol=1e-15)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(97, 131), (2, 5), (3, 3)])
 def test_cuda_sobel_normal_matches_oracle(shape):
