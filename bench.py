@@ -396,7 +396,8 @@ def run_reference(args, cfg, rank, world, device):
         return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * V_per / cb["value"], 2),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "%s (CPU oracle port: compiled reference oracle/_ref not available)" % args.config},
+                "config": {"workload": "%s (CPU oracle port: %s)" % (
+                    args.config, "no CUDA device" if not torch.cuda.is_available() else "compiled reference oracle/_ref not available")},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     ref = build_ref.load()
     my_views = list(range(V_per))
