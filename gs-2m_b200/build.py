@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libgs2m_rasterizer.so")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "binning_v2.cu", "binning_depthfirst.cu", "footprint_masks.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "feature_pack.cu", "postblend.cu", "photometric_loss.cu", "adam.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "binning_depthfirst.cu", "footprint_masks.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "feature_pack.cu", "postblend.cu", "photometric_loss.cu", "adam.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -98,10 +98,7 @@ size_t ImageState::carve(char* base, int W, int H, ImageState* out) {
     carve_array(p, im.final_T, n);
     carve_array(p, im.n_contrib, n);
     carve_array(p, im.ranges, tiles);
-    carve_array(p, im.tile_counts, 2 * tiles);
-    im.tile_cursor = im.tile_counts + tiles;
-    carve_array(p, im.tile_starts, tiles);
-    carve_array(p, im.bin_info, 4);
+    carve_array(p, im.bin_info, BIN_WORDS);
     if (out) *out = im;
     return (size_t)(p - base) + 128;
 }
@@ -117,12 +114,38 @@ static int tile_bits(uint32_t n_tiles) {
 // whichever buffer makes their last digit pass land there (no final copy).
 static int digit_passes(int key_bits) { return (key_bits + 7) / 8; }
 
-enum BinningPath { BIN_DEPTHFIRST = 0, BIN_SORT64 = 1, BIN_RANKED = 2 };
+enum BinningPath { BIN_DEPTHFIRST = 0, BIN_SORT64 = 1 };
 static BinningPath binning_path_from_env() {
     const char* e = getenv("GS2M_BINNING");
     if (e && strcmp(e, "sort64") == 0) return BIN_SORT64;
-    if (e && strcmp(e, "ranked") == 0) return BIN_RANKED;
     return BIN_DEPTHFIRST;
+}
+
+// Host side of the instance-count read-back: a pinned landing buffer and an event per (host thread, device).
+struct HostSlot { uint32_t* pinned; cudaEvent_t ev; };
+static thread_local HostSlot g_slots[64] = {};
+static thread_local long long g_last_R = 0;
+static int host_slot(HostSlot** out) {
+    int dev = 0;
+    GS2M_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d outside 0..63", dev); return GS2M_ERR_INVALID_ARGUMENT; }
+    HostSlot& h = g_slots[dev];
+    if (!h.pinned) {
+        GS2M_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h.pinned), BIN_WORDS * sizeof(uint32_t), cudaHostAllocDefault));
+        GS2M_CUDA(cudaEventCreateWithFlags(&h.ev, cudaEventDisableTiming));
+    }
+    *out = &h;
+    return GS2M_OK;
+}
+
+// discard flags of the control block -> error code (0 when the result is valid)
+static int check_bin_flags(const uint32_t* info, int R_capacity) {
+    const uint32_t flags = info[BIN_FLAGS];
+    g_last_R = (long long)info[BIN_R];
+    if (flags & GS2M_BIN_TOO_LARGE) { set_error("%u or more Gaussian/tile instances exceed the supported 2^30", info[BIN_R]); return GS2M_ERR_TOO_LARGE; }
+    if (flags & GS2M_BIN_PREFILTERED) { set_error("prefiltered was set but a Gaussian is behind the near plane (view-space z <= 0.2)"); return GS2M_ERR_PREFILTERED; }
+    if (flags & GS2M_BIN_OVERFLOW) { set_error("%u instances do not fit R_capacity %d", info[BIN_R], R_capacity); return GS2M_ERR_CAPACITY; }
+    return GS2M_OK;
 }
 
 static int validate_common(int P, int D, int M, int W, int H, int F, const void* means3D, const void* shs,
@@ -199,6 +222,7 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         set_error("forward: missing output / background / opacity pointer"); return GS2M_ERR_INVALID_ARGUMENT;
     }
     if (!a->geometry_buffer || !a->binning_buffer || !a->image_buffer) { set_error("forward: missing resize callbacks"); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (a->R_capacity < 0 || a->R_capacity >= (1 << 30)) { set_error("forward: R_capacity %d outside 0..2^30-1", a->R_capacity); return GS2M_ERR_INVALID_ARGUMENT; }
     cudaStream_t s = (cudaStream_t)a->stream;
 
     FwdParams p;
@@ -218,88 +242,94 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     if (!img_base) { set_error("image_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
     ImageState im;
     ImageState::carve(img_base, p.W, p.H, &im);
+    GS2M_CUDA(cudaMemsetAsync(im.bin_info, 0, BIN_WORDS * sizeof(uint32_t), s));
 
-    int R = 0, V = 0;
-    int max_tile_count = 0;
+    // Binning path (both give bit-identical keys / lists / ranges, tests/test_gpu_parity.py):
+    //   "depthfirst" (default)  depth-sort the visible Gaussians, emit in depth order, 2-pass sort on the tile id
+    //   "sort64"                duplicate + 64-bit onesweep radix sort, the reference's structure (exact mode only)
+    // B200, config 4, binning total: 0.47 / 0.77 ms (profiles/r1_binning_paths.md); GS2M_BINNING=sort64 selects the second.
+    BinningPath path = binning_path_from_env();
+    // exact mode: R is read back before the binning arena is sized (the reference's one host sync).  speculative mode: the
+    // arena is sized for R_capacity and the count-dependent kernels read R / V from the control block on the device.
+    if (a->R_capacity > 0 && path != BIN_DEPTHFIRST) { set_error("forward: speculative mode (R_capacity > 0) needs the default binning path"); return GS2M_ERR_INVALID_ARGUMENT; }
+    const bool speculative = a->R_capacity > 0;
+    int R = 0, R_cap = 0, V_cap = 0;
     GeomState g;
     memset(&g, 0, sizeof(g));
-    const uint32_t* rank_order = nullptr;
-    // Binning path (all three give bit-identical keys / lists / ranges, tests/test_gpu_parity.py):
-    //   "depthfirst" (default)  depth-sort the visible Gaussians, emit in depth order, 2-pass sort on the tile id
-    //   "sort64"                duplicate + 64-bit onesweep radix sort, the reference's structure
-    //   "ranked"                depth-rank + atomic per-tile emission + shared-memory tile sort (binning_v2.cu)
-    // B200, config 4, binning total: 0.47 / 0.77 / 0.56 ms (profiles/r1_binning_paths.md); GS2M_BINNING selects the other two.
-    BinningPath path = binning_path_from_env();
+    HostSlot* slot = nullptr;
     if (p.P > 0) {
         char* geom_base = a->geometry_buffer(a->geometry_user, GeomState::carve(nullptr, p.P, nullptr));
         if (!geom_base) { set_error("geometry_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
         GeomState::carve(geom_base, p.P, &g);
 
-        { StageTimer t(GS2M_STAGE_PREPROCESS_FWD, s); rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, path == BIN_RANKED, s); }
+        { StageTimer t(GS2M_STAGE_PREPROCESS_FWD, s);
+          rc = launch_preprocess_forward(p, g, a->out_radii, a->out_observe, im.bin_info + BIN_FLAGS, a->prefiltered != 0,
+                                         a->no_backward == 0, s); }
         if (rc != GS2M_OK) return rc;
-        uint32_t host_vals[2] = {0, 0};
+        const bool need_host = !(speculative && a->no_wait);
+        if (need_host && (rc = host_slot(&slot)) != GS2M_OK) return rc;
         if (path == BIN_DEPTHFIRST) {
-            // point_offsets + compaction of the visible Gaussians to (depth bits, index) in one scan; {R, V} -> bin_info[2..3]
-            { StageTimer t(GS2M_STAGE_SCAN, s); rc = binning_df_compact(p.P, g, g.depth_keys_alt, g.order_b, im.bin_info + 2, s); }
+            // point_offsets + compaction of the visible Gaussians to (depth bits, index) + the control block in one scan
+            { StageTimer t(GS2M_STAGE_SCAN, s);
+              rc = binning_df_compact(p.P, g, g.depth_keys_alt, g.order_b, im.bin_info,
+                                      speculative ? (uint32_t)a->R_capacity : 0x3FFFFFFFu, s); }
             if (rc != GS2M_OK) return rc;
-            GS2M_CUDA(cudaMemcpyAsync(host_vals, im.bin_info + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (need_host) {
+                GS2M_CUDA(cudaMemcpyAsync(slot->pinned, im.bin_info, BIN_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                GS2M_CUDA(cudaEventRecord(slot->ev, s));
+            }
+            if (speculative) {
+                R_cap = a->R_capacity;
+                V_cap = p.P;
+            } else {
+                GS2M_CUDA(cudaEventSynchronize(slot->ev));
+                if ((rc = check_bin_flags(slot->pinned, 0)) != GS2M_OK) return rc;
+                R = R_cap = (int)slot->pinned[BIN_R];
+                V_cap = (int)slot->pinned[BIN_V];
+            }
         } else {
             { StageTimer t(GS2M_STAGE_SCAN, s); rc = inclusive_sum_u32(g.tiles_touched, g.point_offsets, p.P, g.scan_temp, s); }
             if (rc != GS2M_OK) return rc;
-            // everything of the binning that does not need the instance buffer runs before the host waits for R
-            if (path == BIN_RANKED) {
-                StageTimer t(GS2M_STAGE_SORT, s);
-                rc = binning2_rank_and_count(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, s, &rank_order);
-                if (rc != GS2M_OK) return rc;
-            }
-            GS2M_CUDA(cudaMemcpyAsync(&host_vals[0], g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            if (path == BIN_RANKED) GS2M_CUDA(cudaMemcpyAsync(&host_vals[1], im.bin_info + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            GS2M_CUDA(cudaMemcpyAsync(slot->pinned, im.bin_info, BIN_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            GS2M_CUDA(cudaMemcpyAsync(slot->pinned + BIN_R, g.point_offsets + (p.P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            GS2M_CUDA(cudaStreamSynchronize(s));
+            if (slot->pinned[BIN_R] >= (1u << 30)) slot->pinned[BIN_FLAGS] |= GS2M_BIN_TOO_LARGE;   // 32-bit sum on this path
+            if ((rc = check_bin_flags(slot->pinned, 0)) != GS2M_OK) return rc;
+            R = R_cap = (int)slot->pinned[BIN_R];
         }
-        // the instance count sizes the binning arena: one device->host read, like rasterizer_impl.cu:269-270
-        GS2M_CUDA(cudaStreamSynchronize(s));
-        if (host_vals[0] >= (1u << 30)) { set_error("%u Gaussian/tile instances exceed the supported 2^30", host_vals[0]); return GS2M_ERR_TOO_LARGE; }
-        R = (int)host_vals[0];
-        if (path == BIN_DEPTHFIRST) V = (int)host_vals[1]; else max_tile_count = (int)host_vals[1];
-        if (path == BIN_RANKED && max_tile_count > GS2M_TILE_SORT_CAP) path = BIN_SORT64;   // a tile list too long for shared memory
     }
 
-    char* bin_base = a->binning_buffer(a->binning_user, BinState::carve(nullptr, R, nullptr));
+    char* bin_base = a->binning_buffer(a->binning_user, BinState::carve(nullptr, R_cap, nullptr));
     if (!bin_base) { set_error("binning_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
     BinState b;
-    BinState::carve(bin_base, R, &b);
+    BinState::carve(bin_base, R_cap, &b);
     const uint32_t* point_list = b.point_list;
-    if (R > 0 && path == BIN_DEPTHFIRST) {
+    if (R_cap > 0 && path == BIN_DEPTHFIRST) {
+        const uint32_t* v_used = im.bin_info + BIN_V_USED;
+        const uint32_t* r_used = im.bin_info + BIN_R_USED;
         // depth order of the V visible Gaussians (ties keep ascending index: the compaction is stable and so is the sort)
         int in_input = 0;
         { StageTimer t(GS2M_STAGE_SORT, s);
-          rc = sort_pairs_u32_pingpong(g.depth_keys_alt, g.depth_keys, g.order_b, g.order_a, V, 32, g.rank_temp, s, &in_input); }
+          rc = sort_pairs_u32_pingpong(g.depth_keys_alt, g.depth_keys, g.order_b, g.order_a, V_cap, v_used, 32, g.rank_temp, s, &in_input); }
         if (rc != GS2M_OK) return rc;
         const uint32_t* order = in_input ? g.order_b : g.order_a;
         // 32-bit tile ids ping-pong between the two halves of keys_unsorted; start where the last pass lands in point_list
         int key_bits = 1;
         while (((long long)n_tiles - 1) >> key_bits) ++key_bits;
-        uint32_t* tk[2] = {reinterpret_cast<uint32_t*>(b.keys_unsorted), reinterpret_cast<uint32_t*>(b.keys_unsorted) + R};
+        uint32_t* tk[2] = {reinterpret_cast<uint32_t*>(b.keys_unsorted), reinterpret_cast<uint32_t*>(b.keys_unsorted) + R_cap};
         uint32_t* tv[2] = {b.vals_unsorted, b.point_list};
         const int start = digit_passes(key_bits) & 1 ? 0 : 1;
         { StageTimer t(GS2M_STAGE_DUPLICATE, s);
-          rc = binning_df_emit(V, g, order, a->out_radii, p.tiles_x, p.tiles_y, tk[start], tv[start], s); }
+          rc = binning_df_emit(V_cap, v_used, g, order, a->out_radii, p.tiles_x, p.tiles_y, tk[start], tv[start], s); }
         if (rc != GS2M_OK) return rc;
         { StageTimer t(GS2M_STAGE_SORT, s);
-          rc = sort_pairs_u32_pingpong(tk[start], tk[start ^ 1], tv[start], tv[start ^ 1], R, key_bits, b.sort_temp, s, &in_input); }
+          rc = sort_pairs_u32_pingpong(tk[start], tk[start ^ 1], tv[start], tv[start ^ 1], R_cap, r_used, key_bits, b.sort_temp, s, &in_input); }
         if (rc != GS2M_OK) return rc;
         if ((in_input != 0) != (start == 1)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
         { StageTimer t(GS2M_STAGE_RANGES, s);
-          rc = launch_ranges_masks_keys(R, p.tiles_x, p.tiles_y, tk[1], point_list, g, b.keys_sorted, im.ranges, b.masks, s); }
+          rc = launch_ranges_masks_keys(R_cap, r_used, p.tiles_x, p.tiles_y, tk[1], point_list, g, b.keys_sorted, im.ranges, b.masks, s); }
         if (rc != GS2M_OK) return rc;
-    } else if (R > 0 && path == BIN_RANKED) {
-        { StageTimer t(GS2M_STAGE_SORT, s);
-          rc = binning2_emit_and_sort(p.P, g, a->out_radii, p.tiles_x, p.tiles_y, im, rank_order, b.keys_unsorted, b.keys_sorted,
-                                      b.point_list, max_tile_count, s); }
-        if (rc != GS2M_OK) return rc;
-        // the ranked path already wrote the tile ranges from its per-tile counts
-        { StageTimer t(GS2M_STAGE_RANGES, s); rc = launch_footprint_masks(p.tiles_x, p.tiles_y, im.ranges, point_list, g, b.masks, s); }
-        if (rc != GS2M_OK) return rc;
-    } else if (R > 0) {
+    } else if (R_cap > 0) {
         const int key_bits = 32 + tile_bits((uint32_t)n_tiles);
         uint64_t* kb[2] = {b.keys_unsorted, b.keys_sorted};
         uint32_t* vb[2] = {b.vals_unsorted, b.point_list};
@@ -324,8 +354,17 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
       rc = launch_blend_forward(p, g, point_list, b.masks, im, a->out_color, a->out_observe, a->out_buffer, s); }
     if (rc != GS2M_OK) return rc;
+    if (speculative && p.P > 0) {
+        if (a->no_wait) return a->R_capacity;
+        // everything is queued; the count was ready long before the blend that is now running
+        GS2M_CUDA(cudaEventSynchronize(slot->ev));
+        if ((rc = check_bin_flags(slot->pinned, a->R_capacity)) != GS2M_OK) return rc;
+        R = (int)slot->pinned[BIN_R];
+    }
     return R;
 }
+
+long long gs2m_last_instance_count(void) { return g_last_R; }
 
 int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     if (!a) { set_error("null args"); return GS2M_ERR_INVALID_ARGUMENT; }
@@ -343,8 +382,10 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     }
     if (a->R < 0) { set_error("backward: negative R"); return GS2M_ERR_INVALID_ARGUMENT; }
     if (a->accumulate < 0 || a->accumulate > 2) { set_error("backward: accumulate mode %d outside 0..2", a->accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (a->R_capacity < 0 || (a->R_capacity > 0 && a->R > a->R_capacity)) { set_error("backward: R %d does not fit R_capacity %d", a->R, a->R_capacity); return GS2M_ERR_INVALID_ARGUMENT; }
+    const int R_carve = a->R_capacity > 0 ? a->R_capacity : a->R;    // what forward sized the binning arena for
     if (a->geometry_bytes < GeomState::carve(nullptr, a->P, nullptr) ||
-        a->binning_bytes < BinState::carve(nullptr, a->R, nullptr) ||
+        a->binning_bytes < BinState::carve(nullptr, R_carve, nullptr) ||
         a->image_bytes < ImageState::carve(nullptr, a->width, a->height, nullptr)) {
         set_error("backward: a saved arena is smaller than forward allocated it"); return GS2M_ERR_INVALID_ARGUMENT;
     }
@@ -371,11 +412,14 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     GeomState g;
     GeomState::carve(a->geometry_buffer, p.P, &g);
     BinState b;
-    BinState::carve(a->binning_buffer, p.R, &b);
+    BinState::carve(a->binning_buffer, R_carve, &b);
     ImageState im;
     ImageState::carve(a->image_buffer, p.W, p.H, &im);
     const uint32_t* point_list = b.point_list;
 
+    // The accumulator rows of the visible Gaussians were zeroed by the forward (preprocess); a second backward over the same
+    // forward state has to start from zero again.
+    if (a->grad_acc_dirty) GS2M_CUDA(cudaMemsetAsync(g.grad_acc, 0, (size_t)p.P * GS2M_ACC_STRIDE * sizeof(float), s));
     { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, b.masks, im, s); }
     if (rc != GS2M_OK) return rc;
     { StageTimer t(GS2M_STAGE_PREPROCESS_BWD, s); rc = launch_preprocess_backward(p, g, s); }
@@ -404,6 +448,7 @@ int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buff
         BinState::carve(binning_buffer, R, &b);
         out->keys_sorted = b.keys_sorted;
         out->point_list = b.point_list;
+        out->masks = b.masks;
     }
     if (image_buffer) {
         ImageState im;
@@ -411,6 +456,7 @@ int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buff
         out->final_T = im.final_T;
         out->n_contrib = im.n_contrib;
         out->ranges = reinterpret_cast<const uint32_t*>(im.ranges);
+        out->bin_info = im.bin_info;
     }
     return GS2M_OK;
 }

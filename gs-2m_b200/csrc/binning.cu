@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int R, const 
 }
 
 // ------------------------------------------------------------------ onesweep radix sort ------------------------
+// number of items a count-dependent kernel processes: the host-known capacity, clamped by the device-side count when given
+__device__ __forceinline__ int device_count(int n_cap, const uint32_t* __restrict__ n_ptr) {
+    return n_ptr ? (int)min(*n_ptr, (uint32_t)n_cap) : n_cap;
+}
+
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 12;                       // keys per thread
@@ -151,9 +156,12 @@ constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VALUE_M
 
 // all digit histograms in one pass over the keys
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __restrict__ keys, int n, int n_passes,
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __restrict__ keys, int n_cap,
+                                                                  const uint32_t* __restrict__ n_ptr, int n_passes,
                                                                   int end_bit, uint32_t* __restrict__ hist /*[passes][256]*/) {
     __shared__ uint32_t sh[RS_MAX_PASSES * RS_RADIX];
+    const int n = device_count(n_cap, n_ptr);
+    if ((int)(blockIdx.x * RS_THREADS) >= n) return;
     for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) sh[i] = 0;
     __syncthreads();
     const int stride = gridDim.x * RS_THREADS;
@@ -186,10 +194,15 @@ template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __restrict__ keys_in,
                                                                  KeyT* __restrict__ keys_out,
                                                                  const uint32_t* __restrict__ vals_in,
-                                                                 uint32_t* __restrict__ vals_out, int n, int shift, int bits,
+                                                                 uint32_t* __restrict__ vals_out, int n_cap,
+                                                                 const uint32_t* __restrict__ n_ptr, int shift, int bits,
                                                                  const uint32_t* __restrict__ digit_base /*[256]*/,
                                                                  volatile uint32_t* __restrict__ status /*[tiles][256]*/,
                                                                  uint32_t* __restrict__ ticket) {
+    // The grid covers the capacity; CTAs beyond the real count leave before taking a ticket, so tickets 0..ceil(n/TILE)-1 are
+    // taken by CTAs that do the work (in arrival order) and the look-back never waits for a CTA that exits.
+    const int n = device_count(n_cap, n_ptr);
+    if ((long long)blockIdx.x * RS_TILE >= (long long)n) return;
     __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];
     __shared__ uint32_t s_base[RS_RADIX];       // global index of the tile's first key of a digit, minus its tile-local offset
     __shared__ uint32_t s_tile_off[RS_RADIX];   // tile-local offset of a digit's keys in the staged order
@@ -329,7 +342,7 @@ size_t sort_temp_bytes(int n) {
 // sorted data ended in the *_in buffers (even number of digit passes) — the forward uses this to avoid a copy.
 template <typename KeyT>
 static int sort_pairs_pingpong_t(KeyT* keys_in, KeyT* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
-                                 int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
+                                 const uint32_t* n_ptr, int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
     if (result_in_input) *result_in_input = 0;
     if (n <= 0) return GS2M_OK;
     if (end_bit <= 0 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort_pairs_u64: end_bit %d outside 1..64", end_bit); return GS2M_ERR_INVALID_ARGUMENT; }
@@ -346,7 +359,7 @@ static int sort_pairs_pingpong_t(KeyT* keys_in, KeyT* keys_out, uint32_t* vals_i
     int hist_blocks = (n + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
     count_launches(2 + passes);
-    rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_in, n, passes, end_bit, hist);
+    rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_in, n, n_ptr, passes, end_bit, hist);
     rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
     KeyT* kbuf[2] = {keys_in, keys_out};
     uint32_t* vbuf[2] = {vals_in, vals_out};
@@ -359,7 +372,7 @@ static int sort_pairs_pingpong_t(KeyT* keys_in, KeyT* keys_out, uint32_t* vals_i
     }
     for (int pass = 0; pass < passes; ++pass) {
         const int bits = (end_bit - 8 * pass) < 8 ? (end_bit - 8 * pass) : 8;
-        rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, 0, s>>>(kbuf[src], kbuf[src ^ 1], vbuf[src], vbuf[src ^ 1], n, 8 * pass, bits,
+        rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, 0, s>>>(kbuf[src], kbuf[src ^ 1], vbuf[src], vbuf[src ^ 1], n, n_ptr, 8 * pass, bits,
                                                         hist + pass * RS_RADIX, status + (size_t)pass * tiles * RS_RADIX,
                                                         tickets + pass);
         src ^= 1;
@@ -371,13 +384,13 @@ static int sort_pairs_pingpong_t(KeyT* keys_in, KeyT* keys_out, uint32_t* vals_i
 
 int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
                             int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
-    return sort_pairs_pingpong_t<uint64_t>(keys_in, keys_out, vals_in, vals_out, n, end_bit, temp, s, result_in_input);
+    return sort_pairs_pingpong_t<uint64_t>(keys_in, keys_out, vals_in, vals_out, n, nullptr, end_bit, temp, s, result_in_input);
 }
 
 // 32-bit keys (depth ranking of the Gaussians): same kernels, 4 digit passes.
-int sort_pairs_u32_pingpong(uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
-                            int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
-    return sort_pairs_pingpong_t<uint32_t>(keys_in, keys_out, vals_in, vals_out, n, end_bit, temp, s, result_in_input);
+int sort_pairs_u32_pingpong(uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n_cap,
+                            const uint32_t* n_ptr, int end_bit, char* temp, cudaStream_t s, int* result_in_input) {
+    return sort_pairs_pingpong_t<uint32_t>(keys_in, keys_out, vals_in, vals_out, n_cap, n_ptr, end_bit, temp, s, result_in_input);
 }
 
 int sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit,

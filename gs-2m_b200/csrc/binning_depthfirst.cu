@@ -66,20 +66,48 @@ __global__ void __launch_bounds__(CS_THREADS) compact_tile_sums_kernel(const uin
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the tile sums in place; totals (R, V) to totals[0..1]
-__global__ void __launch_bounds__(CS_THREADS) compact_spine_kernel(uint2* __restrict__ tile_sums, int n_tiles,
-                                                                   uint32_t* __restrict__ totals) {
+// single block: exclusive scan of the tile sums in place.  The number of tile sums is ceil(n / items_per_tile) with n read from
+// device memory when n_ptr is given (the emission's scan runs over the V visible Gaussians, a device-side count).
+// CONTROL: also writes the forward's control block `info` (common.cuh BIN_*): the true instance count R (summed in 64 bits: the
+// 32-bit running offsets may wrap when screen-filling splats push the sum past 2^32) and visible count V, the
+// discard flags, and the counts the later kernels use (zero when the result must be discarded, so that nothing is ever
+// written past the arena).
+template <bool CONTROL>
+__global__ void __launch_bounds__(CS_THREADS) compact_spine_kernel(uint2* __restrict__ tile_sums, int n_cap,
+                                                                   const uint32_t* __restrict__ n_ptr, int items_per_tile,
+                                                                   uint32_t* __restrict__ info, uint32_t R_capacity) {
     __shared__ uint2 sw[8];
+    __shared__ unsigned long long s_total;
+    if (threadIdx.x == 0) s_total = 0ull;
+    const int n = n_ptr ? (int)min(*n_ptr, (uint32_t)n_cap) : n_cap;
+    const int n_tiles = (n + items_per_tile - 1) / items_per_tile;
     uint2 carry = make_uint2(0, 0);
+    unsigned long long wide = 0ull;
     for (int start = 0; start < n_tiles; start += CS_THREADS) {
         const int i = start + threadIdx.x;
         const uint2 v = (i < n_tiles) ? tile_sums[i] : make_uint2(0, 0);
+        wide += v.x;
         uint2 total;
         const uint2 ex = block_exclusive_scan2(v, sw, total);
         if (i < n_tiles) tile_sums[i] = make_uint2(carry.x + ex.x, carry.y + ex.y);
         carry.x += total.x; carry.y += total.y;
     }
-    if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; }
+    if (!CONTROL) return;
+    __syncthreads();
+    atomicAdd(&s_total, wide);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long R64 = s_total;
+        uint32_t flags = info[BIN_FLAGS];                    // GS2M_BIN_PREFILTERED may have been raised by the preprocess
+        if (R64 >= (1ull << 30)) flags |= GS2M_BIN_TOO_LARGE;
+        else if (R64 > (unsigned long long)R_capacity) flags |= GS2M_BIN_OVERFLOW;
+        const bool discard = (flags & (GS2M_BIN_TOO_LARGE | GS2M_BIN_OVERFLOW)) != 0;
+        info[BIN_R] = (uint32_t)min(R64, 0xFFFFFFFFull);
+        info[BIN_V] = carry.y;
+        info[BIN_FLAGS] = flags;
+        info[BIN_R_USED] = discard ? 0u : (uint32_t)R64;
+        info[BIN_V_USED] = discard ? 0u : carry.y;
+    }
 }
 
 __global__ void __launch_bounds__(CS_THREADS) compact_apply_kernel(const uint32_t* __restrict__ tiles_touched,
@@ -118,9 +146,12 @@ constexpr int EMIT_ITEMS = 1;
 constexpr int EMIT_TILE = CS_THREADS * EMIT_ITEMS;
 
 __global__ void __launch_bounds__(CS_THREADS) ordered_tile_sums_kernel(const uint32_t* __restrict__ tiles_touched,
-                                                                       const uint32_t* __restrict__ order, int n,
+                                                                       const uint32_t* __restrict__ order, int n_cap,
+                                                                       const uint32_t* __restrict__ n_ptr,
                                                                        uint2* __restrict__ tile_sums) {
     __shared__ uint2 sw[8];
+    const int n = n_ptr ? (int)min(*n_ptr, (uint32_t)n_cap) : n_cap;
+    if ((int)(blockIdx.x * EMIT_TILE) >= n) return;
     const int base = blockIdx.x * EMIT_TILE + threadIdx.x * EMIT_ITEMS;
     uint2 s = make_uint2(0, 0);
 #pragma unroll
@@ -133,13 +164,16 @@ __global__ void __launch_bounds__(CS_THREADS) ordered_tile_sums_kernel(const uin
 
 // scan apply fused with the emission: thread handles EMIT_ITEMS consecutive depth ranks and writes their instances
 __global__ void __launch_bounds__(CS_THREADS) emit_in_depth_order_kernel(const uint32_t* __restrict__ tiles_touched,
-                                                                         const uint32_t* __restrict__ order, int n,
+                                                                         const uint32_t* __restrict__ order, int n_cap,
+                                                                         const uint32_t* __restrict__ n_ptr,
                                                                          const uint2* __restrict__ tile_offsets,
                                                                          const float4* __restrict__ xy_conic_ab,
                                                                          const int* __restrict__ radii, int tiles_x, int tiles_y,
                                                                          uint32_t* __restrict__ tile_keys,
                                                                          uint32_t* __restrict__ vals) {
     __shared__ uint2 sw[8];
+    const int n = n_ptr ? (int)min(*n_ptr, (uint32_t)n_cap) : n_cap;
+    if ((int)(blockIdx.x * EMIT_TILE) >= n) return;
     const int base = blockIdx.x * EMIT_TILE + threadIdx.x * EMIT_ITEMS;
     uint32_t t[EMIT_ITEMS], id[EMIT_ITEMS];
     uint2 s = make_uint2(0, 0);
@@ -173,31 +207,33 @@ size_t compact_temp_bytes(int n) {
     return (tiles + 1) * sizeof(uint2) + 128;
 }
 
-// stage 1: point_offsets (inclusive scan of tiles_touched) + stable compaction of the visible Gaussians;
-// totals[0] = R (instances), totals[1] = V (visible Gaussians)
-int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals, uint32_t* totals, cudaStream_t s) {
+// stage 1: point_offsets (inclusive scan of tiles_touched) + stable compaction of the visible Gaussians to (depth bits, index)
+// pairs + the control block bin_info (R, V, discard flags; the caller has zeroed it before the preprocess kernel)
+int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals, uint32_t* bin_info, uint32_t R_capacity,
+                       cudaStream_t s) {
     if (P <= 0) return GS2M_OK;
     const int tiles = (P + CS_TILE - 1) / CS_TILE;
     uint2* tile_sums = reinterpret_cast<uint2*>(g.scan_temp);
     count_launches(3);
     compact_tile_sums_kernel<<<tiles, CS_THREADS, 0, s>>>(g.tiles_touched, P, tile_sums);
-    compact_spine_kernel<<<1, CS_THREADS, 0, s>>>(tile_sums, tiles, totals);
+    compact_spine_kernel<true><<<1, CS_THREADS, 0, s>>>(tile_sums, P, nullptr, CS_TILE, bin_info, R_capacity);
     compact_apply_kernel<<<tiles, CS_THREADS, 0, s>>>(g.tiles_touched, g.depths, P, tile_sums, g.point_offsets, keys, vals);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }
 
-// stage 3: instances of the V depth-ordered Gaussians -> (tile id, index) pairs
-int binning_df_emit(int V, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x, int tiles_y,
-                    uint32_t* tile_keys, uint32_t* vals, cudaStream_t s) {
-    if (V <= 0) return GS2M_OK;
-    const int tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
+// stage 3: instances of the depth-ordered visible Gaussians -> (tile id, index) pairs.  The grids cover V_cap Gaussians; the
+// kernels read the real count from n_ptr (device) when given.
+int binning_df_emit(int V_cap, const uint32_t* n_ptr, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x,
+                    int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s) {
+    if (V_cap <= 0) return GS2M_OK;
+    const int tiles = (V_cap + EMIT_TILE - 1) / EMIT_TILE;
     uint2* tile_sums = reinterpret_cast<uint2*>(g.scan_temp);
     count_launches(3);
-    ordered_tile_sums_kernel<<<tiles, CS_THREADS, 0, s>>>(g.tiles_touched, order, V, tile_sums);
-    compact_spine_kernel<<<1, CS_THREADS, 0, s>>>(tile_sums, tiles, reinterpret_cast<uint32_t*>(tile_sums + tiles));
-    emit_in_depth_order_kernel<<<tiles, CS_THREADS, 0, s>>>(g.tiles_touched, order, V, tile_sums, g.xy_conic_ab, radii, tiles_x,
-                                                            tiles_y, tile_keys, vals);
+    ordered_tile_sums_kernel<<<tiles, CS_THREADS, 0, s>>>(g.tiles_touched, order, V_cap, n_ptr, tile_sums);
+    compact_spine_kernel<false><<<1, CS_THREADS, 0, s>>>(tile_sums, V_cap, n_ptr, EMIT_TILE, nullptr, 0u);
+    emit_in_depth_order_kernel<<<tiles, CS_THREADS, 0, s>>>(g.tiles_touched, order, V_cap, n_ptr, tile_sums, g.xy_conic_ab, radii,
+                                                            tiles_x, tiles_y, tile_keys, vals);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }

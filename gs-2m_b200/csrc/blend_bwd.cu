@@ -342,13 +342,14 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
              cudaStream_t s) {
     dim3 grid(p.tiles_x * BWD_CTAS_PER_TILE, p.tiles_y);
     const size_t smem = sizeof(WarpSmemB<F>) * BWD_CTA_WARPS;
-    static std::atomic<bool> configured{false};   // forward/backward may be driven from several host threads
-    if (!configured) {
+    static PerDeviceOnce configured;   // per kernel instantiation and per device; callers may use several host threads
+    int dev;
+    if (configured.need(dev)) {
         GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #ifdef GS2M_BWD_CARVEOUT
         GS2M_CUDA(cudaFuncSetAttribute(blend_backward_kernel<F>, cudaFuncAttributePreferredSharedMemoryCarveout, GS2M_BWD_CARVEOUT));
 #endif
-        configured = true;
+        configured.done(dev);
     }
     count_launches(1);
     blend_backward_kernel<F><<<grid, BWD_CTA_WARPS * 32, smem, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
@@ -363,7 +364,6 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
 
 int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
                           const ImageState& im, cudaStream_t s) {
-    GS2M_CUDA(cudaMemsetAsync(g.grad_acc, 0, (size_t)p.P * GS2M_ACC_STRIDE * sizeof(float), s));
     switch (p.F) {
 #define GS2M_CASE(N) case N: return launch_b<N>(p, g, point_list, masks, im, s);
         GS2M_CASE(0) GS2M_CASE(1) GS2M_CASE(2) GS2M_CASE(3) GS2M_CASE(4) GS2M_CASE(5)

@@ -9,6 +9,7 @@
 // 128-bit loads.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stddef.h>
 #include "../../include/gs2m_rasterizer.h"
@@ -28,10 +29,10 @@ struct GeomState {
     uint32_t* tiles_touched;  // [P]
     uint32_t* point_offsets;  // [P]
     char*     scan_temp;      // gs2m_scan_temp_bytes(P)
-    uint32_t* depth_keys;     // [P] depth bits of visible Gaussians, 0xFFFFFFFF for culled ones (rank sort keys)
-    uint32_t* depth_keys_alt; // [P] ping-pong partner
-    uint32_t* order_a;        // [P] iota on input; rank order (Gaussian index by ascending (depth, index)) after the sort
-    uint32_t* order_b;        // [P] ping-pong partner
+    uint32_t* depth_keys;     // [P] } (depth bits, Gaussian index) of the V visible Gaussians: compaction output and the
+    uint32_t* depth_keys_alt; // [P] } ping-pong buffers of the depth sort
+    uint32_t* order_a;        // [P] }
+    uint32_t* order_b;        // [P] }
     char*     rank_temp;      // sort_temp_bytes(P)
     float*    grad_acc;       // [P,GS2M_ACC_STRIDE] backward blend accumulator
     static size_t carve(char* base, int P, GeomState* out);
@@ -51,12 +52,13 @@ struct ImageState {
     float*    final_T;        // [N]
     uint32_t* n_contrib;      // [N]
     uint2*    ranges;         // [tiles]
-    uint32_t* tile_counts;    // [tiles] instances per tile            } contiguous: one memset clears both
-    uint32_t* tile_cursor;    // [tiles] emission cursors              }
-    uint32_t* tile_starts;    // [tiles] exclusive scan of the counts
-    uint32_t* bin_info;       // [4] {total instances, longest tile list, -, -}
+    uint32_t* bin_info;       // [8] control block written on the device: BIN_* indices below
     static size_t carve(char* base, int W, int H, ImageState* out);
 };
+
+// bin_info words.  R / V are the true counts; R_USED / V_USED are what the count-dependent kernels process: equal to R / V,
+// or 0 when the result has to be discarded anyway (R above the arena's capacity or above the 30-bit sort bookkeeping).
+enum { BIN_R = 0, BIN_V = 1, BIN_FLAGS = 2, BIN_R_USED = 3, BIN_V_USED = 4, BIN_WORDS = 8 };
 
 template <typename T>
 static inline void carve_array(char*& p, T*& ptr, size_t count) {
@@ -75,6 +77,17 @@ struct StageTimer {                         // RAII: cudaEvent pair around one s
 bool check_cuda(cudaError_t e, const char* what);
 #define GS2M_CUDA(call) do { if (!::gs2m::check_cuda((call), #call)) return GS2M_ERR_CUDA; } while (0)
 
+// One-time setup per DEVICE (function attributes such as the dynamic shared-memory opt-in belong to the device's context,
+// not to the process): `if (once.need(dev)) { cudaFuncSetAttribute(...); once.done(dev); }` with dev = cudaGetDevice().
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool need(int& dev) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        return dev >= 64 || !((mask.load(std::memory_order_acquire) >> dev) & 1ull);
+    }
+    void done(int dev) { if (dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+
 // ---- stage launchers (each defined in its own .cu) ----
 struct FwdParams {
     int P, D, M, W, H, F;
@@ -84,22 +97,25 @@ struct FwdParams {
     const float *viewmatrix, *projmatrix, *cam_pos, *background;
 };
 
-int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, bool rank_keys, cudaStream_t s);
+int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, uint32_t* bin_flags,
+                              bool prefiltered, bool zero_grad_acc, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y,
                                uint64_t* keys, uint32_t* vals, cudaStream_t s);
 int launch_identify_tile_ranges(int R, const uint64_t* keys_sorted, uint2* ranges, int n_tiles, cudaStream_t s);
 int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* keys_sorted, const uint32_t* point_list,
                             const GeomState& g, uint2* ranges, uint8_t* masks, cudaStream_t s);
-int launch_ranges_masks_keys(int R, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted, const uint32_t* point_list,
-                             const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks, cudaStream_t s);
+// Count-dependent stages take a capacity (`*_cap`: sizes the grid) and a device pointer to the real count (`n_ptr`, may be
+// nullptr = the capacity is the count); the kernels process min(*n_ptr, cap) items.
+int launch_ranges_masks_keys(int R_cap, const uint32_t* n_ptr, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted,
+                             const uint32_t* point_list, const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks,
+                             cudaStream_t s);
 // depth-first binning (binning_depthfirst.cu)
 size_t compact_temp_bytes(int n);
-int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals, uint32_t* totals, cudaStream_t s);
-int binning_df_emit(int V, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x, int tiles_y,
-                    uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
-int launch_footprint_masks(int tiles_x, int tiles_y, const uint2* ranges, const uint32_t* point_list, const GeomState& g,
-                           uint8_t* masks, cudaStream_t s);
+int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals, uint32_t* bin_info, uint32_t R_capacity,
+                       cudaStream_t s);
+int binning_df_emit(int V_cap, const uint32_t* n_ptr, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x,
+                    int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
 int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
                          const ImageState& im, float* out_color, int* out_observe, float* out_buffer, cudaStream_t s);
 
@@ -125,14 +141,8 @@ int sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uin
                    char* temp, cudaStream_t s);
 int sort_pairs_u64_pingpong(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
                             int end_bit, char* temp, cudaStream_t s, int* result_in_input);
-int sort_pairs_u32_pingpong(uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n,
-                            int end_bit, char* temp, cudaStream_t s, int* result_in_input);
-int binning2_rank_and_count(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y, const ImageState& im,
-                            cudaStream_t s, const uint32_t** order_out);
-int binning2_emit_and_sort(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y, const ImageState& im,
-                           const uint32_t* order, uint64_t* tmp, uint64_t* keys_out, uint32_t* vals_out, int max_count,
-                           cudaStream_t s);
-constexpr int GS2M_TILE_SORT_CAP = 8192;   // longest tile list the shared-memory tile sort takes (else: global 64-bit sort)
+int sort_pairs_u32_pingpong(uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n_cap,
+                            const uint32_t* n_ptr, int end_bit, char* temp, cudaStream_t s, int* result_in_input);
 size_t scan_temp_bytes(int n);
 int inclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, char* temp, cudaStream_t s);
 

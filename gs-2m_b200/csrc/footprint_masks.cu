@@ -8,29 +8,18 @@
 namespace gs2m {
 namespace {
 
-__global__ void __launch_bounds__(256) footprint_mask_kernel(int tiles_x, const uint2* __restrict__ ranges,
-                                                             const uint32_t* __restrict__ point_list,
-                                                             const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
-                                                             uint8_t* __restrict__ masks) {
-    const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
-    const int px0 = blockIdx.x * GS2M_TILE_X, py0 = blockIdx.y * GS2M_TILE_Y;
-    for (uint32_t i = range.x + threadIdx.x; i < range.y; i += 256) {
-        const uint32_t gid = point_list[i];
-        const CullRecord cr = make_cull_record(__ldg(rec_a + gid), __ldg(rec_b + gid));
-        masks[i] = (uint8_t)warp_block_mask(cr, px0, py0);
-    }
-}
-
-// Same masks, one thread per instance, fused with the tile-range identification of the 64-bit-sort path
+// One thread per instance, fused with the tile-range identification
 // (identifyTileRanges, rasterizer_impl.cu:108-129): the sorted key gives the tile, the sorted value the Gaussian.
 // KeyT = uint64_t: the reference's (tile << 32 | depth) keys.  KeyT = uint32_t: bare tile ids of the depth-first binning
 // path; the 64-bit key of every instance is then re-materialised into keys64_out (the parity surface of the sort).
 template <typename KeyT>
-__global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R, int tiles_x, const KeyT* __restrict__ keys,
+__global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R_cap, const uint32_t* __restrict__ n_ptr, int tiles_x,
+                                                               const KeyT* __restrict__ keys,
                                                                const uint32_t* __restrict__ point_list,
                                                                const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
                                                                const float* __restrict__ depths, uint64_t* __restrict__ keys64_out,
                                                                uint2* __restrict__ ranges, uint8_t* __restrict__ masks) {
+    const int R = n_ptr ? (int)min(*n_ptr, (uint32_t)R_cap) : R_cap;   // grid covers the capacity, the count lives on the device
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     constexpr int SHIFT = sizeof(KeyT) == 8 ? 32 : 0;
@@ -59,7 +48,7 @@ int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* key
     GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
     if (R > 0) {
         count_launches(1);
-        ranges_and_masks_kernel<uint64_t><<<(R + 255) / 256, 256, 0, s>>>(R, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
+        ranges_and_masks_kernel<uint64_t><<<(R + 255) / 256, 256, 0, s>>>(R, nullptr, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
                                                                           g.conic_c_opac, nullptr, nullptr, ranges, masks);
         GS2M_CUDA(cudaGetLastError());
     }
@@ -67,23 +56,17 @@ int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* key
 }
 
 // depth-first binning: sorted 32-bit tile ids in, ranges + masks + the 64-bit (tile | depth) keys out
-int launch_ranges_masks_keys(int R, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted, const uint32_t* point_list,
-                             const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks, cudaStream_t s) {
+int launch_ranges_masks_keys(int R_cap, const uint32_t* n_ptr, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted,
+                             const uint32_t* point_list, const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks,
+                             cudaStream_t s) {
     GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
-    if (R > 0) {
+    if (R_cap > 0) {
         count_launches(1);
-        ranges_and_masks_kernel<uint32_t><<<(R + 255) / 256, 256, 0, s>>>(R, tiles_x, tile_keys_sorted, point_list, g.xy_conic_ab,
-                                                                          g.conic_c_opac, g.depths, keys64_out, ranges, masks);
+        ranges_and_masks_kernel<uint32_t><<<(R_cap + 255) / 256, 256, 0, s>>>(R_cap, n_ptr, tiles_x, tile_keys_sorted, point_list,
+                                                                              g.xy_conic_ab, g.conic_c_opac, g.depths, keys64_out,
+                                                                              ranges, masks);
         GS2M_CUDA(cudaGetLastError());
     }
-    return GS2M_OK;
-}
-
-int launch_footprint_masks(int tiles_x, int tiles_y, const uint2* ranges, const uint32_t* point_list, const GeomState& g,
-                           uint8_t* masks, cudaStream_t s) {
-    count_launches(1);
-    footprint_mask_kernel<<<dim3(tiles_x, tiles_y), 256, 0, s>>>(tiles_x, ranges, point_list, g.xy_conic_ab, g.conic_c_opac, masks);
-    GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }
 

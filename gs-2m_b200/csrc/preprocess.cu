@@ -122,10 +122,14 @@ __device__ __forceinline__ void sh_to_rgb(int D, float x, float y, float z, Load
     }
 }
 
-// RANK_KEYS: also write the (depth bits, iota) pairs the "ranked" binning path sorts (binning_v2.cu)
-template <bool RANK_KEYS>
+// ZERO_ACC: also zero the backward accumulator row of every visible Gaussian (the backward blend adds into it with vector
+// reductions; rows of culled Gaussians are never read) — replaces a memset of the whole [P,24] array in the backward.
+// `bin_flags`: when `prefiltered` is set the caller has promised that no Gaussian fails the near-plane test; one that does
+// raises GS2M_BIN_PREFILTERED (the reference printf()s and traps the device there, auxiliary.h:154-160).
+template <bool ZERO_ACC>
 __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, GeomState g, int* __restrict__ radii,
-                                                                 int* __restrict__ observe) {
+                                                                 int* __restrict__ observe, uint32_t* __restrict__ bin_flags,
+                                                                 bool prefiltered) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
 
@@ -144,17 +148,16 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
     radii[idx] = 0;
     observe[idx] = 0;
     g.tiles_touched[idx] = 0;
-    if (RANK_KEYS) {
-        g.depth_keys[idx] = 0xFFFFFFFFu;   // culled Gaussians rank behind every visible one
-        g.order_a[idx] = (uint32_t)idx;
-    }
 
     const float* __restrict__ vm = p.viewmatrix;
     const float* __restrict__ pm = p.projmatrix;
 
     // near-plane cull on view-space depth (auxiliary.h:150-152; the x/y frustum test is disabled in the reference)
     const float depth = __fadd_rn(dot3m(px, py, pz, vm[2], vm[6], vm[10]), vm[14]);
-    if (depth <= 0.2f) return;
+    if (depth <= 0.2f) {
+        if (prefiltered) atomicOr(bin_flags, (uint32_t)GS2M_BIN_PREFILTERED);
+        return;
+    }
 
     // clip-space position and perspective divide
     const float hx = __fadd_rn(dot3m(px, py, pz, pm[0], pm[4], pm[8]), pm[12]);
@@ -264,12 +267,16 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(FwdParams p, Ge
     const float thr = (opacity >= 0.00392156885936856f) ? 2.0f * logf(255.0f * opacity) : -1.0f;
 
     g.depths[idx] = depth;
-    if (RANK_KEYS) g.depth_keys[idx] = __float_as_uint(depth);
     radii[idx] = radius;
     g.xy_conic_ab[idx] = make_float4(pix_x, pix_y, conic_x, conic_y);
     g.conic_c_opac[idx] = make_float4(conic_z, opacity, thr, 0.0f);
     g.rgb[idx] = rgb;
     g.tiles_touched[idx] = n_tiles;
+    if (ZERO_ACC) {
+        float4* acc = reinterpret_cast<float4*>(g.grad_acc + (size_t)idx * GS2M_ACC_STRIDE);
+#pragma unroll
+        for (int i = 0; i < GS2M_ACC_STRIDE / 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -283,11 +290,12 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 }  // namespace
 
-int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, bool rank_keys, cudaStream_t s) {
+int launch_preprocess_forward(const FwdParams& p, const GeomState& g, int* radii, int* observe, uint32_t* bin_flags,
+                              bool prefiltered, bool zero_grad_acc, cudaStream_t s) {
     if (p.P == 0) return GS2M_OK;
     count_launches(1);
-    if (rank_keys) preprocess_forward_kernel<true><<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe);
-    else preprocess_forward_kernel<false><<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe);
+    if (zero_grad_acc) preprocess_forward_kernel<true><<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe, bin_flags, prefiltered);
+    else preprocess_forward_kernel<false><<<(p.P + 255) / 256, 256, 0, s>>>(p, g, radii, observe, bin_flags, prefiltered);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }

@@ -493,12 +493,13 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
     count_launches(1);
     if (p.accumulate < 0 || p.accumulate > 2) { set_error("accumulate mode %d outside 0..2", p.accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
     if (p.M <= 16) {
-        static std::atomic<bool> configured{false};
-        if (!configured) {
+        static PerDeviceOnce configured;
+        int dev;
+        if (configured.need(dev)) {
             GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
             GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
             GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
-            configured = true;
+            configured.done(dev);
         }
         if (p.accumulate == 1) preprocess_backward_staged_kernel<1><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
         else if (p.accumulate == 2) preprocess_backward_staged_kernel<2><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);

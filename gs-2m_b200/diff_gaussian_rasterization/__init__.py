@@ -17,6 +17,7 @@ one-process-per-GPU data parallelism works unchanged.  There is no CPU path.
 Extras beyond the reference surface (used by the view-sharded data-parallel step and by the parity tests):
 ``forward_raw`` / ``backward_raw`` (explicit-state calls with in-place gradient accumulation) and ``state_view``.
 """
+import os
 from typing import NamedTuple, Optional
 
 import torch
@@ -86,17 +87,48 @@ class _Arena:
             return None
 
 
-class RasterState(NamedTuple):
-    """What backward needs from forward (the reference keeps the same things in ``ctx``, binding ``:86-88``)."""
-    num_rendered: int
-    geom: torch.Tensor
-    binning: torch.Tensor
-    img: torch.Tensor
+class RasterState:
+    """What backward needs from forward (the reference keeps the same things in ``ctx``, binding ``:86-88``).
+    ``capacity`` is the instance capacity the binning arena was sized for when the forward ran speculatively (0: it was sized
+    for ``num_rendered`` itself); ``backward_runs`` counts the backward passes already made over this state (the library
+    clears its accumulator again from the second one on)."""
+    __slots__ = ("num_rendered", "geom", "binning", "img", "capacity", "backward_runs", "prepared")
+
+    def __init__(self, num_rendered, geom, binning, img, capacity=0, prepared=True):
+        self.num_rendered, self.geom, self.binning, self.img = num_rendered, geom, binning, img
+        self.capacity, self.backward_runs, self.prepared = capacity, 0, prepared
+
+
+# Instance-count hints for the speculative forward, per (device, width, height): the largest count of the recent calls.
+# The binning arena is sized for the hint plus a margin and nothing waits for the host; a view that needs more is detected
+# by the library (GS2M_ERR_CAPACITY) and simply re-run in exact mode.  GS2M_EXACT_BINNING=1 disables the speculation.
+_R_HINT = {}
+_R_MARGIN = 1.25
+
+
+def _capacity_for(key):
+    if os.environ.get("GS2M_EXACT_BINNING") == "1" or os.environ.get("GS2M_BINNING", "depthfirst") != "depthfirst":
+        return 0
+    hint = _R_HINT.get(key, 0)
+    if hint <= 0:
+        return 0
+    return min(int(hint * _R_MARGIN) + 65536, (1 << 30) - 1)
+
+
+def _note_instances(key, R):
+    # decay slowly so that one outlier view does not pin the arena size forever
+    _R_HINT[key] = max(int(R), int(_R_HINT.get(key, 0) * 0.98))
 
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, features,
-                raster_settings: GaussianRasterizationSettings):
-    """Run the forward pipeline. Returns ``(color, radii, observe, buffer, RasterState)``."""
+                raster_settings: GaussianRasterizationSettings, for_backward=True, capacity=None, no_wait=False):
+    """Run the forward pipeline. Returns ``(color, radii, observe, buffer, RasterState)``.
+
+    ``capacity`` (instances): None = automatic (speculative once a previous call on this device and image size has told the
+    instance count, exact otherwise), 0 = exact mode (host reads the count back before the binning arena is sized, like the
+    reference), > 0 = speculative with that capacity.  ``no_wait`` (needs an explicit capacity) never touches the host, so
+    the call can be captured in a CUDA graph; ``state.num_rendered`` is then the capacity and the caller checks
+    ``state_view(...)["bin_info"]``.  ``for_backward=False`` skips preparing the backward accumulator (inference)."""
     lib = _native.load()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:52-54
@@ -124,6 +156,12 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         raise RuntimeError("features must have dimensions (num_points, %d)" % NUM_FEATURES)
     M = int(shs_t.shape[1]) if shs_t is not None else 0
 
+    key = (dev.index, W, H)
+    auto = capacity is None
+    if auto:
+        capacity = _capacity_for(key) if P > 0 else 0
+    if no_wait and capacity <= 0:
+        raise RuntimeError("no_wait needs an explicit instance capacity")
     with torch.cuda.device(dev):
         color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
         buffer = torch.empty((NUM_FEATURES, H, W), dtype=torch.float32, device=dev)
@@ -132,6 +170,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
         a = _native.ForwardArgs()
         a.geometry_buffer, a.binning_buffer, a.image_buffer = geom.callback, binning.callback, img.callback
+        a.R_capacity, a.no_wait, a.no_backward = int(capacity), int(bool(no_wait)), int(not for_backward)
         a.P, a.D, a.M = P, int(rs.sh_degree), M
         a.background = _ptr(bg)
         a.width, a.height = W, H
@@ -144,13 +183,22 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         a.out_color, a.out_radii, a.out_observe, a.out_buffer = _ptr(color), _ptr(radii), _ptr(observe), _ptr(buffer)
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         try:
-            num_rendered = _native.check(lib.gs2m_rasterize_forward(a), "gs2m_rasterize_forward")
+            try:
+                num_rendered = _native.check(lib.gs2m_rasterize_forward(a), "gs2m_rasterize_forward")
+            except RasterizerError as e:
+                if not (auto and e.code == _native.ERR_CAPACITY):
+                    raise
+                # this view has more instances than the hint allowed for: run it again with the exact count
+                a.R_capacity = capacity = 0
+                num_rendered = _native.check(lib.gs2m_rasterize_forward(a), "gs2m_rasterize_forward")
         finally:
             # the ctypes callback holds a bound method of its arena: break that reference cycle now so the arenas
             # (hundreds of MB each) are released by reference counting, not whenever the cyclic GC next runs
             a.geometry_buffer = a.binning_buffer = a.image_buffer = _native.RESIZE_FN()
             geom.callback = binning.callback = img.callback = None
-    state = RasterState(num_rendered, geom.tensor, binning.tensor, img.tensor)
+    if not no_wait and P > 0:
+        _note_instances(key, num_rendered)
+    state = RasterState(num_rendered, geom.tensor, binning.tensor, img.tensor, capacity=int(capacity), prepared=bool(for_backward))
     return color, radii, observe, buffer, state
 
 
@@ -204,11 +252,19 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
         if accumulate:
             raise RuntimeError("accumulate=True needs caller-provided gradient tensors")
         grads = alloc_grads(P, M, dev)
+    for name, c in _GRAD_SHAPES + (("dL_dsh", 3 * M),):
+        t = grads.get(name)
+        if name == "dL_dsh" and M == 0:
+            continue
+        if t is None or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * c:
+            raise RuntimeError("grads[%r] must be a contiguous float32 tensor with %d x %d elements on %s" % (name, P, c, dev))
     if P == 0:
         return grads
     with torch.cuda.device(dev):
         b = _native.BackwardArgs()
-        b.P, b.D, b.M, b.R = P, int(rs.sh_degree), M, int(state.num_rendered)
+        b.P, b.D, b.M, b.R, b.R_capacity = P, int(rs.sh_degree), M, int(state.num_rendered), int(state.capacity)
+        b.grad_acc_dirty = int(state.backward_runs > 0 or not state.prepared)
+        state.backward_runs += 1
         b.background = _ptr(bg)
         b.width, b.height = W, H
         b.means3D, b.shs, b.colors_precomp, b.scales = _ptr(means3D), _ptr(shs_t), _ptr(col_t), _ptr(sca_t)
@@ -254,13 +310,13 @@ def update_view_stats(radii, observe, max_radii2D=None, observe_cnt=None):
 
 def state_view(P, raster_settings, state: RasterState):
     """Typed tensors aliasing the opaque arenas (tests only): depths, rec_a, rec_b, rgb, cov3D, clamped,
-    tiles_touched, point_offsets, grad_acc, keys_sorted, point_list, final_T, n_contrib, ranges."""
+    tiles_touched, point_offsets, grad_acc, keys_sorted, point_list, masks, final_T, n_contrib, ranges, bin_info."""
     lib = _native.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     R = int(state.num_rendered)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     v = _native.StateView()
-    _native.check(lib.gs2m_state_view_get(P, W, H, R, _ptr(state.geom) if P else None,
+    _native.check(lib.gs2m_state_view_get(P, W, H, int(state.capacity) or R, _ptr(state.geom) if P else None,
                                           _ptr(state.binning) if state.binning.numel() else None,
                                           _ptr(state.img), v), "gs2m_state_view_get")
 
@@ -285,6 +341,8 @@ def state_view(P, raster_settings, state: RasterState):
         out["grad_acc"] = view(g, v.grad_acc, _native.ACC_STRIDE * P, torch.float32).view(P, _native.ACC_STRIDE)
     out["keys_sorted"] = view(bn, v.keys_sorted, R, torch.int64)
     out["point_list"] = view(bn, v.point_list, R, torch.int32)
+    out["masks"] = view(bn, v.masks, R, torch.uint8)
+    out["bin_info"] = view(im, v.bin_info, 8, torch.int32)
     out["final_T"] = view(im, v.final_T, H * W, torch.float32).view(H, W)
     out["n_contrib"] = view(im, v.n_contrib, H * W, torch.int32).view(H, W)
     out["ranges"] = view(im, v.ranges, 2 * tiles, torch.int32).view(tiles, 2)
@@ -298,10 +356,12 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features,
                 raster_settings):
+        needs_grad = any(ctx.needs_input_grad)      # inference calls (torch.no_grad) skip the backward preparation
         color, radii, observe, buffer, state = forward_raw(
-            means3D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features, raster_settings)
+            means3D, shs, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features, raster_settings,
+            for_backward=needs_grad)
         ctx.raster_settings = raster_settings
-        ctx.num_rendered = state.num_rendered
+        ctx.raster_state = state
         ctx.save_for_backward(means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp, features, radii,
                               state.geom, state.binning, state.img)
         ctx.mark_non_differentiable(radii, observe)
@@ -311,7 +371,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, grad_color, _grad_radii, _grad_observe, grad_buffer):
         (means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp, features, radii,
          geom, binning, img) = ctx.saved_tensors
-        state = RasterState(ctx.num_rendered, geom, binning, img)
+        state = ctx.raster_state      # (the arenas travel through save_for_backward so that autograd tracks their lifetime)
         g = backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp,
                          features, radii, ctx.raster_settings, state)
         # slots: means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features, settings

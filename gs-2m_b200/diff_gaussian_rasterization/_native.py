@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GS2M_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgs2m_rasterizer.so")
 
+ABI_VERSION = 3
 NUM_CHANNELS = 3
 NUM_FEATURES = 10
 ACC_STRIDE = 24
@@ -34,12 +35,13 @@ class ForwardArgs(C.Structure):
         ("prefiltered", C.c_int), ("feature_count", C.c_int),
         ("out_color", _fp), ("out_radii", _fp), ("out_observe", _fp), ("out_buffer", _fp),
         ("stream", C.c_void_p),
+        ("R_capacity", C.c_int), ("no_wait", C.c_int), ("no_backward", C.c_int),
     ]
 
 
 class BackwardArgs(C.Structure):
     _fields_ = [
-        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int),
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int), ("R_capacity", C.c_int),
         ("background", _fp),
         ("width", C.c_int), ("height", C.c_int),
         ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("scales", _fp),
@@ -56,6 +58,7 @@ class BackwardArgs(C.Structure):
         ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscale", _fp), ("dL_drot", _fp), ("dL_dfeatures", _fp),
         ("accumulate", C.c_int),
         ("stream", C.c_void_p),
+        ("grad_acc_dirty", C.c_int),
         ("densify_grad_accum", _fp), ("densify_grad_accum_abs", _fp), ("densify_denom", _fp),
     ]
 
@@ -68,7 +71,7 @@ class AdamGroup(C.Structure):
 class StateView(C.Structure):
     _fields_ = [(n, _fp) for n in (
         "depths", "rec_a", "rec_b", "rgb", "cov3D", "clamped", "tiles_touched", "point_offsets", "grad_acc",
-        "keys_sorted", "point_list", "final_T", "n_contrib", "ranges")]
+        "keys_sorted", "point_list", "masks", "final_T", "n_contrib", "ranges", "bin_info")]
 
 
 # every symbol include/gs2m_rasterizer.h declares: (name, restype, argtypes)
@@ -77,6 +80,7 @@ EXPORTS = [
     ("gs2m_last_error", C.c_char_p, []),
     ("gs2m_rasterize_forward", C.c_int, [C.POINTER(ForwardArgs)]),
     ("gs2m_rasterize_backward", C.c_int, [C.POINTER(BackwardArgs)]),
+    ("gs2m_last_instance_count", C.c_longlong, []),
     ("gs2m_geometry_bytes", C.c_size_t, [C.c_int]),
     ("gs2m_image_bytes", C.c_size_t, [C.c_int, C.c_int]),
     ("gs2m_binning_bytes", C.c_size_t, [C.c_int]),
@@ -129,18 +133,24 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the header and the library diverge
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.gs2m_abi_version() != 2:
+    if lib.gs2m_abi_version() != ABI_VERSION:
         raise ImportError("libgs2m_rasterizer.so ABI version mismatch")
     _lib = lib
     return lib
 
 
+ERR_CAPACITY = -5   # GS2M_ERR_CAPACITY: a speculative forward saw more instances than its R_capacity
+BIN_OVERFLOW, BIN_PREFILTERED, BIN_TOO_LARGE = 1, 2, 4
+
+
 class RasterizerError(RuntimeError):
-    pass
+    code = 0
 
 
 def check(rc, what):
     if rc < 0:
         msg = load().gs2m_last_error().decode("utf-8", "replace")
-        raise RasterizerError("%s failed (code %d): %s" % (what, rc, msg))
+        err = RasterizerError("%s failed (code %d): %s" % (what, rc, msg))
+        err.code = rc
+        raise err
     return rc

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS2M_ABI_VERSION 2
+#define GS2M_ABI_VERSION 3
 
 /* compile-time constants of the path (reference: cuda_rasterizer/config.h:15-18) */
 #define GS2M_NUM_CHANNELS 3
@@ -42,7 +42,11 @@ enum {
     GS2M_ERR_INVALID_ARGUMENT = -1, /* bad sizes / missing required pointer / feature_count outside 0..10 */
     GS2M_ERR_ALLOC = -2,            /* a resize callback returned NULL */
     GS2M_ERR_CUDA = -3,             /* CUDA runtime error (message in gs2m_last_error) */
-    GS2M_ERR_TOO_LARGE = -4         /* instance count does not fit the 30-bit sort bookkeeping */
+    GS2M_ERR_TOO_LARGE = -4,        /* instance count does not fit the 30-bit sort bookkeeping (counted in 64 bits) */
+    GS2M_ERR_CAPACITY = -5,         /* speculative forward: more instances than R_capacity; outputs are invalid, call again
+                                       with a larger capacity (gs2m_last_instance_count() gives the count) or in exact mode */
+    GS2M_ERR_PREFILTERED = -6       /* `prefiltered` was set but a Gaussian failed the near-plane test; the reference traps the
+                                       device here (auxiliary.h:154-160), this library reports a checked error instead */
 };
 
 /* Resize callback: make the arena at least `bytes` long and return its (>=128-B aligned) device base pointer.
@@ -72,20 +76,38 @@ typedef struct gs2m_forward_args {
     const float* projmatrix;    /* [4,4] row-major tensor of (P*W2V)^T */
     const float* cam_pos;       /* [3] */
     float tan_fovx, tan_fovy;
-    int prefiltered;            /* reference traps on a culled Gaussian when set; we report GS2M_ERR via debug flag only */
+    int prefiltered;            /* caller promises that no Gaussian is behind the near plane: a culled one is an error
+                                   (GS2M_ERR_PREFILTERED; the reference printf()s and __trap()s, auxiliary.h:154-160) */
     int feature_count;          /* 0..10: prefix length of `features` columns that are blended */
     float* out_color;           /* [3,H,W]   fully written (no pre-zeroing needed) */
     int*   out_radii;           /* [P]       fully written */
     int*   out_observe;         /* [P]       fully written */
     float* out_buffer;          /* [10,H,W]  fully written (channels >= feature_count are zero) */
     void*  stream;              /* cudaStream_t */
+    /* How the instance count R (known only on the device after the per-Gaussian stage) sizes the binning arena.
+     *   R_capacity == 0  exact mode: R is read back (one host sync before the R-dependent launches, like
+     *                    rasterizer_impl.cu:269-270) and binning_buffer is asked for gs2m_binning_bytes(R).  Returns R.
+     *   R_capacity  > 0  speculative mode: binning_buffer is asked for gs2m_binning_bytes(R_capacity) up front, every
+     *                    R-dependent kernel is launched on a grid sized for the capacity and reads the real count from device
+     *                    memory, so no launch waits for the host.  With no_wait == 0 the call then waits for the count (which
+     *                    finished long before the blend it has just queued) and returns R, or GS2M_ERR_CAPACITY /
+     *                    GS2M_ERR_TOO_LARGE / GS2M_ERR_PREFILTERED when the result must be discarded.  With no_wait == 1 the
+     *                    host is never touched (the call can be captured into a CUDA graph); it returns R_capacity and the
+     *                    caller checks gs2m_state_view.bin_info later.  Backward must be given the same R_capacity. */
+    int R_capacity;
+    int no_wait;
+    int no_backward;            /* 1: inference only — skip preparing (zeroing) the backward accumulator rows of the visible Gaussians */
 } gs2m_forward_args;
+
+/* Instance count seen by the calling thread's most recent forward that waited for it (exact mode or no_wait == 0). */
+long long gs2m_last_instance_count(void);
 
 int gs2m_rasterize_forward(const gs2m_forward_args* args);
 
 /* ---- backward: replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:58-90, rasterizer_impl.cu:334-438) ---- */
 typedef struct gs2m_backward_args {
     int P, D, M, R;             /* R = value returned by forward */
+    int R_capacity;             /* the forward's R_capacity (0 = exact mode: the binning arena was sized for R itself) */
     const float* background;
     int width, height;
     const float* means3D;
@@ -125,6 +147,9 @@ typedef struct gs2m_backward_args {
     float* dL_dfeatures;        /* [P,10] */
     int accumulate;
     void* stream;
+    int grad_acc_dirty;         /* 0 for the first backward after a forward (which zeroed the internal accumulator rows of the
+                                   visible Gaussians); 1 when backward runs again over the same forward state, or when the
+                                   forward ran with no_backward: the library then clears the accumulator first */
     /* optional (NULL = off): GS-2M's densification statistics, fused into the per-Gaussian backward so that they see the
      * gradient of THIS view even in accumulate mode (scene/gaussian_model.py:569-573 add_densification_stats with
      * update_filter = radii > 0): accum += |dL_dmeans2D.xy|, accum_abs += |dL_dmeans2D.zw|, denom += 1.  float[P] each,
@@ -157,14 +182,17 @@ typedef struct gs2m_state_view {
     const uint32_t* tiles_touched;
     const uint32_t* point_offsets;  /* inclusive scan of tiles_touched */
     const float*    grad_acc;       /* [P,24] packed backward-blend accumulator (valid after backward) */
-    /* binning arena, [R] */
+    /* binning arena, [R] (pass the arena's capacity as `R` when forward ran in speculative mode) */
     const uint64_t* keys_sorted;    /* (tile << 32) | float_bits(depth) */
     const uint32_t* point_list;     /* sorted Gaussian indices */
+    const uint8_t*  masks;          /* footprint mask of every list entry: bit w = warp block w of the tile may blend it */
     /* image arena */
     const float*    final_T;        /* [H*W] */
     const uint32_t* n_contrib;      /* [H*W] */
     const uint32_t* ranges;         /* [tiles,2] */
+    const uint32_t* bin_info;       /* [8] {R, V, flags, R used by the kernels, V used, -, -, -}; flags: GS2M_BIN_* */
 } gs2m_state_view;
+enum { GS2M_BIN_OVERFLOW = 1, GS2M_BIN_PREFILTERED = 2, GS2M_BIN_TOO_LARGE = 4 };
 
 int gs2m_state_view_get(int P, int width, int height, int R,
                         char* geometry_buffer, char* binning_buffer, char* image_buffer, gs2m_state_view* out);

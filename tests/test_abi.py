@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     for name in declared_functions():
         assert hasattr(lib, name), "symbol %s declared in the header but missing from the library" % name
     lib.gs2m_abi_version.restype = ctypes.c_int
-    assert lib.gs2m_abi_version() == 2
+    assert lib.gs2m_abi_version() == 3
 
 
 def test_ctypes_binding_covers_the_header(lib_path):

@@ -145,12 +145,15 @@ def test_sh_degrees_and_coefficient_counts(dgr, ref, deg, M):
         assert err <= 5e-4, "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
 
 
-@pytest.mark.parametrize("path", ["depthfirst", "ranked", "sort64"])
+@pytest.mark.parametrize("path", ["depthfirst", "depthfirst-exact", "sort64"])
 def test_all_binning_paths_are_bit_exact(dgr, ref, path, monkeypatch):
-    """GS2M_BINNING selects depth sort + emission in depth order + tile sort (default), duplicate + 64-bit onesweep sort, or
-    depth-rank + per-tile shared-memory sort; keys, lists and ranges must be bit-identical to the reference with each
-    (includes huge rectangles, a one-tile image = 1 tile-key bit, a 256-tile image = one digit pass, and depth ties)."""
-    monkeypatch.setenv("GS2M_BINNING", path)
+    """GS2M_BINNING selects depth sort + emission in depth order + tile sort (default; speculative from the second call on,
+    or exact with GS2M_EXACT_BINNING=1) or duplicate + 64-bit onesweep sort; keys, lists and ranges must be bit-identical
+    to the reference with each (includes huge rectangles, a one-tile image = 1 tile-key bit, a 256-tile image = one digit
+    pass, and depth ties)."""
+    monkeypatch.setenv("GS2M_BINNING", path.split("-")[0])
+    if path.endswith("exact"):
+        monkeypatch.setenv("GS2M_EXACT_BINNING", "1")
     for P, W, H, F, scale_big in ((60_000, 640, 400, 10, 1.0), (4_000, 330, 210, 5, 60.0), (900, 16, 16, 3, 1.0),
                                   (20_000, 256, 256, 2, 1.0)):
         scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
@@ -163,8 +166,151 @@ def test_all_binning_paths_are_bit_exact(dgr, ref, path, monkeypatch):
             m[1::2] = m[0::2]
             scene = scene._replace(means3D=m.contiguous())
         r = helpers.run_reference(ref, scene, cam, feats, F)
-        o = helpers.run_ours(dgr, scene, cam, feats, F)
-        assert_forward_bit_exact(o, r, P)
+        for _ in range(2):      # the second call of the default path runs speculatively (instance-count hint from the first)
+            o = helpers.run_ours(dgr, scene, cam, feats, F)
+            assert_forward_bit_exact(o, r, P)
+
+
+def test_speculative_forward_modes(dgr, ref):
+    """The forward without a host round trip: binning arena sized from a capacity, count-dependent kernels on
+    capacity-sized grids that read R / V from device memory.  Same bits as the exact mode and the reference for any sufficient
+    capacity; a capacity that is too small is reported (explicit capacity) or transparently re-run (automatic mode);
+    no_wait never touches the host and leaves the verdict in bin_info."""
+    from diff_gaussian_rasterization import _native
+    P, W, H, F = 30_000, 400, 300, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    settings = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    args = (scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, feats, settings)
+    r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+    R = int(r["R"])
+    exact = dgr.forward_raw(*args, capacity=0)
+    assert exact[4].num_rendered == R and exact[4].capacity == 0
+    g_exact = dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats, exact[1],
+                               settings, exact[4])
+    for cap in (R, R + 1, 2 * R + 12345, 40 * R):
+        color, radii, observe, buffer, state = dgr.forward_raw(*args, capacity=cap)
+        assert state.num_rendered == R and state.capacity == cap
+        sv = dgr.state_view(P, settings, state)
+        assert sv["bin_info"][:5].tolist() == [R, int((r["radii"] > 0).sum()), 0, R, int((r["radii"] > 0).sum())]
+        assert torch.equal(sv["keys_sorted"], r["keys_sorted"]) and torch.equal(sv["point_list"], r["point_list"])
+        assert torch.equal(sv["ranges"], r["ranges"]) and torch.equal(sv["n_contrib"], r["n_contrib"])
+        assert torch.equal(helpers.bits(color), helpers.bits(exact[0])) and torch.equal(helpers.bits(buffer), helpers.bits(exact[3]))
+        assert torch.equal(observe, r["observe"])
+        g = dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats, radii,
+                             settings, state)
+        for k in GRAD_NAMES:    # two runs of the same kernels: only the order of the vector reductions differs
+            err, _ = helpers.grad_errors(g[k], g_exact[k])
+            assert err <= (5e-4 if k in ILL_CONDITIONED else 1e-5), "%s capacity %d: %.3e" % (k, cap, err)
+    # explicit capacity that is too small: checked error, nothing written past the arena
+    with pytest.raises(dgr.RasterizerError) as ei:
+        dgr.forward_raw(*args, capacity=R - 1)
+    assert ei.value.code == _native.ERR_CAPACITY and _native.load().gs2m_last_instance_count() == R
+    # automatic mode recovers by itself
+    key = (torch.cuda.current_device(), W, H)
+    dgr._R_HINT[key] = 10
+    color, radii, observe, buffer, state = dgr.forward_raw(*args)
+    assert state.num_rendered == R and state.capacity == 0 and dgr._R_HINT[key] == R
+    assert torch.equal(helpers.bits(color), helpers.bits(exact[0]))
+    color, radii, observe, buffer, state = dgr.forward_raw(*args)
+    assert state.num_rendered == R and state.capacity >= R and torch.equal(helpers.bits(color), helpers.bits(exact[0]))
+    # no_wait: capturable, verdict on the device
+    color, radii, observe, buffer, state = dgr.forward_raw(*args, capacity=R + 1000, no_wait=True)
+    sv = dgr.state_view(P, settings, state)
+    assert state.num_rendered == R + 1000 and sv["bin_info"][:4].tolist() == [R, int((radii > 0).sum()), 0, R]
+    assert torch.equal(helpers.bits(color), helpers.bits(exact[0]))
+    color, radii, observe, buffer, state = dgr.forward_raw(*args, capacity=R // 2, no_wait=True)
+    sv = dgr.state_view(P, settings, state)
+    assert sv["bin_info"][0].item() == R and sv["bin_info"][2].item() == _native.BIN_OVERFLOW and sv["bin_info"][3].item() == 0
+    assert float(buffer.abs().max()) == 0.0      # discarded result: nothing was blended
+
+
+def test_forward_under_cuda_graph(dgr, ref):
+    """no_wait forward + backward captured in a CUDA graph and replayed with new camera matrices in the static buffers."""
+    P, W, H, F = 20_000, 320, 240, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6, n_views=2)
+    _, cam1, feats1, _, _ = helpers.make_view(P, W, H, F, shell=0.6, view=1, n_views=2)
+    st_cam = syn.Camera(H, W, cam.tanfovx, cam.tanfovy, cam.world_view_transform.clone(), cam.full_proj_transform.clone(),
+                        cam.camera_center.clone())
+    st_feats = feats.clone()
+    settings = syn.raster_settings_for(st_cam, F, dgr.GaussianRasterizationSettings)
+    args = (scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, st_feats, settings)
+    cap = 4 * int(dgr.forward_raw(*args, capacity=0)[4].num_rendered)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):      # warm-up on the capture stream (one-time function attributes, allocator pools)
+        out = dgr.forward_raw(*args, capacity=cap, no_wait=True)
+        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, st_feats, out[1], settings, out[4])
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        color, radii, observe, buffer, state = dgr.forward_raw(*args, capacity=cap, no_wait=True)
+        g = dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, st_feats, radii,
+                             settings, state)
+    for c, f in ((cam1, feats1), (cam, feats)):
+        st_cam.world_view_transform.copy_(c.world_view_transform)
+        st_cam.full_proj_transform.copy_(c.full_proj_transform)
+        st_cam.camera_center.copy_(c.camera_center)
+        st_feats.copy_(f)
+        graph.replay()
+        torch.cuda.synchronize()
+        r = helpers.run_reference(ref, scene, c, f, F, gc, gb)
+        assert torch.equal(radii, r["radii"]) and torch.equal(observe, r["observe"])
+        torch.testing.assert_close(color, r["color"], rtol=RENDER_RTOL, atol=RENDER_ATOL)
+        torch.testing.assert_close(buffer, r["buffer"], rtol=RENDER_RTOL, atol=RENDER_ATOL)
+        for k in ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dfeatures"):
+            err, _ = helpers.grad_errors(g[k], r[k])
+            assert err <= 1e-5, "%s %.3e" % (k, err)
+
+
+def test_backward_twice_and_inference_forward(dgr):
+    """The forward zeroes the backward accumulator rows of the visible Gaussians; a second backward over the same state, or a
+    backward after an inference-only forward, must clear it again (grad_acc_dirty)."""
+    P, W, H, F = 9000, 200, 150, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    settings = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    args = (scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, feats, settings)
+    bargs = (scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats)
+    color, radii, observe, buffer, state = dgr.forward_raw(*args)
+    g1 = {k: v.clone() for k, v in dgr.backward_raw(gc, gb, *bargs, radii, settings, state).items()}
+    g2 = dgr.backward_raw(gc, gb, *bargs, radii, settings, state)
+    color, radii, observe, buffer, state_inf = dgr.forward_raw(*args, for_backward=False)
+    g3 = dgr.backward_raw(gc, gb, *bargs, radii, settings, state_inf)
+    for k in GRAD_NAMES:
+        for other in (g2, g3):
+            err, _ = helpers.grad_errors(other[k], g1[k])
+            assert err <= (5e-4 if k in ILL_CONDITIONED else 1e-5), "%s %.3e" % (k, err)
+
+
+def test_prefiltered_is_a_checked_error(dgr):
+    """The reference traps the device when `prefiltered` is set and a Gaussian fails the near-plane test
+    (auxiliary.h:154-160); here it is a checked error, in exact and in speculative mode."""
+    from diff_gaussian_rasterization import _native
+    scene, cam, feats, _, _ = helpers.make_view(20_000, 160, 120, 5, cam_radius=0.5)      # camera inside the cloud
+    settings = syn.raster_settings_for(cam, 5, dgr.GaussianRasterizationSettings)
+    args = (scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, feats)
+    R = dgr.forward_raw(*args, settings, capacity=0)[4].num_rendered
+    for cap in (0, R + 100):
+        with pytest.raises(dgr.RasterizerError) as ei:
+            dgr.forward_raw(*args, settings._replace(prefiltered=True), capacity=cap)
+        assert ei.value.code == -6
+    # everything in front of the camera: the flag is harmless
+    scene2, cam2, feats2, _, _ = helpers.make_view(5_000, 160, 120, 5, cam_radius=4.0)
+    st2 = syn.raster_settings_for(cam2, 5, dgr.GaussianRasterizationSettings)._replace(prefiltered=True)
+    dgr.forward_raw(scene2.means3D, scene2.shs, None, scene2.opacities, scene2.scales, scene2.rotations, None, feats2, st2)
+
+
+def test_second_device_in_one_process(dgr):
+    """Function attributes (dynamic shared-memory opt-in) and the host read-back slot are per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        scene, cam, feats, gc, gb = helpers.make_view(8000, 200, 150, 10, shell=0.6, device=dev)
+        o = helpers.run_ours(dgr, scene, cam, feats, 10, gc, gb)
+        outs.append({k: o[k].cpu() for k in ("color", "radii", "dL_dmeans3D", "dL_dsh")})
+    for o in outs[1:]:
+        assert torch.equal(o["radii"], outs[0]["radii"]) and torch.equal(o["color"], outs[0]["color"])
+        assert helpers.grad_errors(o["dL_dsh"], outs[0]["dL_dsh"])[0] <= 1e-5
 
 
 def test_precomputed_colors_and_covariances(dgr, ref):
