@@ -105,7 +105,12 @@ __global__ void __launch_bounds__(LTHREADS) ssim_l1_backward_kernel(int H, int W
                                                                     const float* __restrict__ dm_dE1,
                                                                     const float* __restrict__ dm_dE11,
                                                                     const float* __restrict__ dm_dE12, float g_map, float g_l1,
+                                                                    const float* __restrict__ upstream_dev,
                                                                     float* __restrict__ dL_drender) {
+    if (upstream_dev != nullptr) {      // upstream gradient that lives on the device: no host read in the caller's backward
+        const float u = __ldg(upstream_dev);
+        g_map *= u; g_l1 *= u;
+    }
     __shared__ float sd[3][LH][LH + 1];
     __shared__ float hz[3][LH][LT];
     const int ch = blockIdx.z;
@@ -180,7 +185,7 @@ int gs2m_photometric_loss_forward(int channels, int height, int width, const flo
 
 int gs2m_photometric_loss_backward(int channels, int height, int width, const float* render, const float* gt, const float* dm_dE1,
                                    const float* dm_dE11, const float* dm_dE12, float lambda_ssim, float upstream,
-                                   float* dL_drender, void* stream) {
+                                   const float* upstream_device, float* dL_drender, void* stream) {
     if (channels <= 0 || height <= 0 || width <= 0 || !render || !gt || !dm_dE1 || !dm_dE11 || !dm_dE12 || !dL_drender) {
         set_error("photometric_loss_backward: bad arguments"); return GS2M_ERR_INVALID_ARGUMENT;
     }
@@ -189,7 +194,8 @@ int gs2m_photometric_loss_backward(int channels, int height, int width, const fl
     count_launches(1);
     ssim_l1_backward_kernel<<<grid, LTHREADS, 0, (cudaStream_t)stream>>>(height, width, render, gt, gaussian_window(), dm_dE1, dm_dE11,
                                                                          dm_dE12, -lambda_ssim * upstream * inv_n,
-                                                                         (1.0f - lambda_ssim) * upstream * inv_n, dL_drender);
+                                                                         (1.0f - lambda_ssim) * upstream * inv_n, upstream_device,
+                                                                         dL_drender);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }

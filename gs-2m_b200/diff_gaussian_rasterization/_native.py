@@ -98,7 +98,7 @@ EXPORTS = [
     ("gs2m_sobel_normal_forward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [_fp] * 5 + [C.c_void_p]),
     ("gs2m_sobel_normal_backward", C.c_int, [C.c_int, C.c_int] + [C.c_float] * 4 + [_fp] * 7 + [C.c_void_p]),
     ("gs2m_photometric_loss_forward", C.c_int, [C.c_int] * 3 + [_fp] * 6 + [C.c_void_p]),
-    ("gs2m_photometric_loss_backward", C.c_int, [C.c_int] * 3 + [_fp] * 5 + [C.c_float, C.c_float, _fp, C.c_void_p]),
+    ("gs2m_photometric_loss_backward", C.c_int, [C.c_int] * 3 + [_fp] * 5 + [C.c_float, C.c_float, _fp, _fp, C.c_void_p]),
     ("gs2m_adam_step", C.c_int, [C.POINTER(AdamGroup), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     ("gs2m_view_stats_update", C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]),
     ("gs2m_profile_enable", None, [C.c_int]),

@@ -217,10 +217,12 @@ class _PhotometricLoss(torch.autograd.Function):
         dev = render.device
         C_, H, W = (int(d) for d in render.shape)
         grad = torch.empty_like(render)
+        # the incoming gradient stays on the device (no host read: the step pipeline stays asynchronous and capturable)
+        up = g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         with torch.cuda.device(dev):
             _native.check(lib.gs2m_photometric_loss_backward(C_, H, W, render.data_ptr(), gt.data_ptr(), maps[0].data_ptr(),
                                                              maps[1].data_ptr(), maps[2].data_ptr(), ctx.lambda_ssim,
-                                                             float(g_loss), grad.data_ptr(),
+                                                             1.0, up.data_ptr(), grad.data_ptr(),
                                                              torch.cuda.current_stream(dev).cuda_stream),
                           "gs2m_photometric_loss_backward")
         return grad, None, None
@@ -259,9 +261,40 @@ class FusedAdam:
             if g["name"] == name:
                 g["lr"] = float(lr)
 
+    # ---- optimizer-state surgery of GS-2M's densification (scene/gaussian_model.py:372-403, 437-456): every method returns
+    # {name: new parameter tensor}, like the reference's helpers return ``optimizable_tensors`` ----
+    def replace_tensor(self, tensor, name):
+        """``replace_tensor_to_optimizer`` (reset_opacity): new parameter values, moments back to zero."""
+        out = {}
+        for g in self.groups:
+            if g["name"] == name:
+                g["param"] = tensor.detach().contiguous()
+                g["exp_avg"], g["exp_avg_sq"] = torch.zeros_like(g["param"]), torch.zeros_like(g["param"])
+                out[name] = g["param"]
+        return out
+
+    def prune(self, valid_mask):
+        """``_prune_optimizer``: keep the rows where ``valid_mask`` is true, in parameters and moments."""
+        out = {}
+        for g in self.groups:
+            g["param"] = g["param"][valid_mask].contiguous()
+            g["exp_avg"], g["exp_avg_sq"] = g["exp_avg"][valid_mask].contiguous(), g["exp_avg_sq"][valid_mask].contiguous()
+            out[g["name"]] = g["param"]
+        return out
+
+    def cat(self, tensors_dict):
+        """``cat_tensors_to_optimizer`` (densification_postfix): append new rows; their moments start at zero."""
+        out = {}
+        for g in self.groups:
+            ext = tensors_dict[g["name"]].detach().to(g["param"])
+            g["param"] = torch.cat((g["param"], ext), dim=0).contiguous()
+            g["exp_avg"] = torch.cat((g["exp_avg"], torch.zeros_like(ext)), dim=0)
+            g["exp_avg_sq"] = torch.cat((g["exp_avg_sq"], torch.zeros_like(ext)), dim=0)
+            out[g["name"]] = g["param"]
+        return out
+
     def step(self, grads):
         lib = _native.load()
-        self.t += 1
         arr = (_native.AdamGroup * len(self.groups))()
         dev = self.groups[0]["param"].device
         for k, g in enumerate(self.groups):
@@ -270,6 +303,9 @@ class FusedAdam:
             width = p.numel() // max(rows, 1)
             if gr.dtype != torch.float32 or gr.device != p.device or gr.numel() != p.numel() or int(gr.shape[0]) != rows:
                 raise RuntimeError("FusedAdam: gradient of %s does not match its parameter" % g["name"])
+            if g["exp_avg"].shape != p.shape or g["exp_avg_sq"].shape != p.shape or not p.is_contiguous():
+                raise RuntimeError("FusedAdam: state of %s does not match its parameter (resize with prune / cat / replace_tensor)"
+                                   % g["name"])
             if gr.is_contiguous():
                 stride, off_ptr = width, gr.data_ptr()
             else:   # a column slice of a wider row-major block: rows keep the parent's stride, the inner part is dense
@@ -284,6 +320,7 @@ class FusedAdam:
             a = arr[k]
             a.param, a.exp_avg, a.exp_avg_sq, a.grad = p.data_ptr(), g["exp_avg"].data_ptr(), g["exp_avg_sq"].data_ptr(), off_ptr
             a.rows, a.width, a.grad_row_stride, a.grad_col_offset, a.lr = rows, width, stride, 0, float(g["lr"])
+        self.t += 1          # (after validation: a rejected call does not advance the bias correction)
         with torch.cuda.device(dev):
             _native.check(lib.gs2m_adam_step(arr, len(self.groups), self.t, self.betas[0], self.betas[1], self.eps,
                                              torch.cuda.current_stream(dev).cuda_stream), "gs2m_adam_step")

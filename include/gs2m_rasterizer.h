@@ -264,12 +264,14 @@ int gs2m_sobel_normal_backward(int width, int height, float fx, float fy, float 
  * and :30-70: 11x11 Gaussian window, sigma 1.5, zero "same" padding, per channel, C1 = 0.01^2, C2 = 0.03^2 — what the
  * fused-ssim submodule computes).  Images are [channels,H,W].  forward: sums[0] += sum|render - gt|, sums[1] += sum SSIM (the
  * caller zeroes `sums` and forms the means), and the three [channels,H,W] derivative maps the backward needs.  backward:
- * dL_drender = upstream * dLrgb/drender — directly the `grad_color` of gs2m_rasterize_backward. */
+ * dL_drender = upstream * dLrgb/drender — directly the `grad_color` of gs2m_rasterize_backward.  The upstream gradient is
+ * `upstream` times, when `upstream_device` is not NULL, the float it points to in device memory (an autograd caller passes
+ * its incoming gradient tensor there and never reads it on the host). */
 int gs2m_photometric_loss_forward(int channels, int height, int width, const float* render, const float* gt, float* dm_dE1,
                                   float* dm_dE11, float* dm_dE12, float* sums, void* stream);
 int gs2m_photometric_loss_backward(int channels, int height, int width, const float* render, const float* gt, const float* dm_dE1,
                                    const float* dm_dE11, const float* dm_dE12, float lambda_ssim, float upstream,
-                                   float* dL_drender, void* stream);
+                                   const float* upstream_device, float* dL_drender, void* stream);
 
 /* ---- one Adam step over all parameter groups in a single launch ----
  * torch.optim.Adam(groups, eps=1e-15) of scene/gaussian_model.py:230-242: default betas, per-group learning rate, no weight decay,

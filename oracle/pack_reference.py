@@ -6,8 +6,11 @@ Follows (paths relative to /root/reference):
   scene/gaussian_model.py:146-160         get_normals (argmin one-hot, bmm with build_rotation, in-place flip, normalise)
   utils/general_utils.py:72-92            build_rotation
   gaussian_renderer/__init__.py:82-96     cam_normals, cam_points, features columns
-The reference's own modules cannot be imported here (scene/__init__.py pulls plyfile, simple_knn, nvdiffrast — SURVEY.md
-section 8c), so parity for this stage is "unpinned by reference tests": it is anchored on this line-by-line restatement.
+Pinning: the reference ships no tests for these stages, so every function here is checked against the reference's OWN code,
+imported from /root/reference with stubbed third-party modules: directly on the CPU where the tree is
+present (tests/test_caller_oracle_pinned.py) and through committed vectors generated from it
+(tests/golden/caller_stage_golden.npz by tests/golden/make_caller_golden.py; tests/golden/facade_*.npz by
+tests/golden/make_facade_golden.py, the real render() around the compiled reference rasterizer on a B200).
 """
 import torch
 
@@ -100,10 +103,10 @@ def sobel_normal_map(depth, alpha, bg_color, world_view_transform, fx, fy, cx, c
     H, W = depth.shape
     intrinsic = torch.tensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=depth.dtype, device=depth.device)
     extrinsic = world_view_transform.transpose(0, 1).contiguous()
-    valid_x = torch.arange(W, dtype=torch.float32, device=depth.device).to(depth.dtype) / (W - 1)
-    valid_y = torch.arange(H, dtype=torch.float32, device=depth.device).to(depth.dtype) / (H - 1)
+    valid_x = torch.arange(W, dtype=torch.float32, device=depth.device) / (W - 1)      # divided in float32 whatever the depth's
+    valid_y = torch.arange(H, dtype=torch.float32, device=depth.device) / (H - 1)      # dtype is (normal_utils.py:14-15)
     valid_x, valid_y = torch.meshgrid(valid_x, valid_y, indexing="xy")
-    ndc_xyz = torch.stack([valid_x, valid_y, depth], dim=-1)
+    ndc_xyz = torch.stack([valid_x.to(depth.dtype), valid_y.to(depth.dtype), depth], dim=-1)
     inv_scale = torch.tensor([[W - 1, H - 1]], dtype=depth.dtype, device=depth.device)
     cam_z = ndc_xyz[..., 2:3]
     cam_xy = ndc_xyz[..., :2] * inv_scale * cam_z
@@ -118,3 +121,34 @@ def sobel_normal_map(depth, alpha, bg_color, world_view_transform, fx, fy, cx, c
     xyz_normal = torch.nn.functional.pad(xyz_normal.permute(2, 0, 1), (1, 1, 1, 1), mode="constant").permute(1, 2, 0)
     normal_ref = xyz_normal * alpha[..., None] + bg_color[None, None, ...] * (1.0 - alpha[..., None])
     return normal_ref.permute(2, 0, 1)
+
+
+def render_like(rasterizer, raw, shs, wvt, full_proj, campos, tanfovx, tanfovy, W, H, bg, active_sh_degree=3,
+                geometry_stage=False, material_stage=False, sobel_normal=False, blend_metallic=False, z_depth=False):
+    """The render facade (gaussian_renderer/__init__.py:21-175) restated with the functions of this file around a rasterizer
+    module that has the reference's Python surface: activations + packing (:49-96), settings (:98-110), the rasterizer call
+    (:113-123), the post-blend maps (:125-141), the result dict (:143-158) and the depth-derived normal (:160-175).
+    ``raw`` holds the nine raw parameter tensors (xyz, scaling, rotation, opacity, albedo, roughness, metallic) and ``shs`` the
+    (P,16,3) SH block; everything differentiable through autograd.  Pinned against the real facade by tests/golden/facade_*.npz."""
+    P = raw["xyz"].shape[0]
+    screenspace_points = torch.zeros((P, 4), dtype=raw["xyz"].dtype, requires_grad=True, device=raw["xyz"].device) + 0
+    screenspace_points.retain_grad()
+    scales, rotations, opacity, features = activate_and_pack(
+        raw["xyz"], raw["scaling"], raw["rotation"], raw["opacity"], raw["albedo"], raw["roughness"], raw["metallic"], wvt,
+        campos, z_depth=z_depth, blend_metallic=blend_metallic)
+    feature_count = (9 if material_stage else 5 if geometry_stage else 1) + (1 if blend_metallic else 0)
+    settings = rasterizer.GaussianRasterizationSettings(
+        image_height=int(H), image_width=int(W), tanfovx=tanfovx, tanfovy=tanfovy, bg=bg, scale_modifier=1.0, viewmatrix=wvt,
+        projmatrix=full_proj, sh_degree=active_sh_degree, campos=campos, prefiltered=False, feature_count=feature_count)
+    rendered_image, radii, observe, buffer = rasterizer.GaussianRasterizer(raster_settings=settings)(
+        means3D=raw["xyz"], means2D=screenspace_points, opacities=opacity, shs=shs, colors_precomp=None, scales=scales,
+        rotations=rotations, cov3D_precomp=None, features=features)
+    fx, fy = W / (2.0 * tanfovx), H / (2.0 * tanfovy)
+    local_normal_map, depth_map, normal_mask = derive_maps(buffer, wvt, fx, fy, 0.5 * W, 0.5 * H, z_depth=z_depth)
+    out = {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+           "observe": observe, "alpha_map": buffer[0:1], "distance_map": None if z_depth else buffer[1:2], "depth_map": depth_map,
+           "normal_map": buffer[2:5], "albedo_map": buffer[5:8], "roughness_map": buffer[8:9], "metallic_map": buffer[9:10],
+           "normal_mask": normal_mask, "local_normal_map": local_normal_map}
+    if sobel_normal:
+        out["sobel_map"] = sobel_normal_map(out["depth_map"].squeeze(0), out["alpha_map"][0], bg, wvt, fx, fy, 0.5 * W, 0.5 * H)
+    return out

@@ -27,7 +27,13 @@ class Settings(NamedTuple):
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Rasterizer vectors (make_golden.py); the facade_* / caller_* files next to them have their own loaders."""
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith(("facade_", "caller_")))
+
+
+def facade_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "facade_*.npz")))
 
 
 def load(path, device="cpu", settings_cls=Settings):

@@ -211,3 +211,53 @@ def test_cuda_sobel_normal_matches_oracle(shape):
     torch.testing.assert_close(alpha.grad.cpu().double(), alpha64.grad, rtol=2e-4, atol=2e-4)
     a, b = depth.grad.cpu().double(), depth64.grad
     assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-6
+
+
+@pytest.mark.gpu
+def test_fused_adam_follows_densification_state_surgery():
+    """prune / cat / replace_tensor mirror _prune_optimizer, cat_tensors_to_optimizer and replace_tensor_to_optimizer
+    (scene/gaussian_model.py:372-403, 437-456): after each, FusedAdam keeps stepping like torch.optim.Adam whose state got the
+    reference's surgery."""
+    from diff_gaussian_rasterization.packing import FusedAdam
+    g = torch.Generator().manual_seed(33)
+    P = 4001
+    shapes = {"xyz": (3,), "opacity": (1,), "f_rest": (15, 3)}
+    lrs = {"xyz": 1.6e-4, "opacity": 0.05, "f_rest": 1.25e-4}
+    params = {k: torch.nn.Parameter(torch.randn((P,) + s, generator=g).cuda()) for k, s in shapes.items()}
+    opt = torch.optim.Adam([{"params": [params[k]], "lr": lrs[k], "name": k} for k in shapes], lr=0.0, eps=1e-15)
+    fused = FusedAdam([{"name": k, "param": params[k].detach().clone(), "lr": lrs[k]} for k in shapes])
+
+    def both_step():
+        n = fused.groups[0]["param"].shape[0]
+        grads = {k: torch.randn((n,) + s, generator=g).cuda() for k, s in shapes.items()}
+        for grp in opt.param_groups:
+            grp["params"][0].grad = grads[grp["name"]].clone()
+        opt.step()
+        fused.step(grads)
+
+    def surgery(fn):
+        for grp in opt.param_groups:
+            old = grp["params"][0]
+            st = opt.state.pop(old)
+            new_p, st["exp_avg"], st["exp_avg_sq"] = fn(grp["name"], old.detach(), st["exp_avg"], st["exp_avg_sq"])
+            grp["params"][0] = torch.nn.Parameter(new_p.requires_grad_(True))
+            opt.state[grp["params"][0]] = st
+
+    both_step(); both_step()
+    with pytest.raises(RuntimeError, match="does not match"):
+        fused.step({k: torch.zeros((P - 1,) + s).cuda() for k, s in shapes.items()})     # stale size is an error, not a wild write
+    keep = (torch.rand(P, generator=g) > 0.3).cuda()
+    surgery(lambda n, p, m, v: (p[keep], m[keep], v[keep]))
+    out = fused.prune(keep)
+    assert out["xyz"].shape[0] == int(keep.sum())
+    both_step()
+    ext = {k: torch.randn((257,) + s, generator=g).cuda() for k, s in shapes.items()}
+    surgery(lambda n, p, m, v: (torch.cat((p, ext[n])), torch.cat((m, torch.zeros_like(ext[n]))), torch.cat((v, torch.zeros_like(ext[n])))))
+    fused.cat(ext)
+    both_step()
+    new_op = torch.randn(fused.groups[1]["param"].shape, generator=g).cuda()
+    surgery(lambda n, p, m, v: (new_op.clone(), torch.zeros_like(m), torch.zeros_like(v)) if n == "opacity" else (p, m, v))
+    fused.replace_tensor(new_op.clone(), "opacity")
+    both_step(); both_step()
+    for grp, fg in zip(opt.param_groups, fused.groups):
+        torch.testing.assert_close(fg["param"], grp["params"][0].detach(), rtol=2e-6, atol=2e-7, msg=grp["name"])
