@@ -3,9 +3,11 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config tnt-3m] [--views-per-rank V]
 
-A *step* is one view-sharded batch: every rank rasterizes (forward + backward, gradients accumulated in place) its
-V views of the N*V-view batch and, for N > 1, the per-Gaussian parameter gradients are summed with NCCL all-reduce.
-Per-GPU work is fixed as N grows (weak scaling).  Prints ONE JSON line (see DESIGN.md "Measurement").
+A *step* is one view-sharded batch: every rank renders (forward + backward, gradients accumulated in place into the nine
+raw parameter-gradient groups) its V views of the N*V-view batch and, for N > 1, those parameter gradients are summed with
+NCCL all-reduce, Gaussian range by Gaussian range under the remaining backward work.  Per-GPU work is fixed as N grows (weak
+scaling).  Prints ONE JSON line (see DESIGN.md "Measurement"); at N > 1 it carries `dp_check`: the all-reduced gradients of
+one step against the same rank running the whole batch sequentially.
 
 `--impl reference` times the unmodified reference CUDA rasterizer (compiled into oracle/_ref by oracle/build_ref.py)
 through its own Python binding on the same workload (rank 0 only; the reference has no multi-GPU path); when that
@@ -105,32 +107,72 @@ def build_workload(cfg, n_views_total, my_views, device):
 def run_ours(args, cfg, rank, world, device):
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization import _native
+    from diff_gaussian_rasterization.packing import activate_and_pack
     import view_parallel as vp
     lib = _native.load()
     P, W, H, F, M = cfg["P"], cfg["W"], cfg["H"], cfg["F"], 16
     V_per = args.views_per_rank
     n_views = world * V_per
     my_views = list(vp.shard_views(n_views, world, rank))
-    scene, cams_cpu, cams, feats, gc, gb = build_workload(cfg, n_views, my_views, device)
-    settings = {v: syn.raster_settings_for(cams[v], F, dgr.GaussianRasterizationSettings) for v in my_views}
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"]), device)
+    cams_cpu = syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])
+    cams = {v: syn.camera_to(cams_cpu[v], device) for v in range(n_views)}       # all views: dp_check replays the whole batch
+    settings = {v: syn.raster_settings_for(cams[v], F, dgr.GaussianRasterizationSettings) for v in range(n_views)}
+    gc, gb = (t.to(device) for t in syn.make_upstream_grads(W, H, F))
+    raw = syn.raw_parameters(scene)
+    order = ("xyz", "scaling", "rotation", "opacity", "albedo", "roughness", "metallic")
+    blend_metallic = F in (2, 6, 10)
     stats = {}
-
-    def render_view(v, buckets, accumulate):
-        st = settings[v]
-        color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
-                                                               scene.scales, scene.rotations, None, feats[v], st)
-        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], radii,
-                         st, state, grads=buckets.tensors, accumulate=accumulate, densify_stats=holder["step"].stats.backward_args())
-        stats["R"], stats["radii"] = state.num_rendered, radii
-        return {"radii": radii, "observe": observe}
-
     holder = {}
-    step = holder["step"] = vp.ViewShardedStep(P, M, device, render_view, world=world, rank=rank, n_streams=args.streams)
+
+    # ---- the training-faithful chain: the features and the activated scale / rotation / opacity depend on the
+    # camera, so every view runs  fused activation+packing forward -> rasterizer forward -> reverse blend  as soon as it is
+    # scheduled, and the per-Gaussian backward + fused packing backward (+= into the nine RAW parameter-gradient groups, 64
+    # floats per Gaussian) afterwards, Gaussian range by Gaussian range, each finished range all-reduced under the next one.
+    def begin_view(v, grad_color=None, st=None):
+        st = st or settings[v]
+        with torch.no_grad():
+            s_, q_, o_, f_ = activate_and_pack(*[raw[k] for k in order], st.viewmatrix, st.campos, blend_metallic=blend_metallic)
+        color, radii, observe, buffer, state = dgr.forward_raw(raw["xyz"], scene.shs, None, o_, s_, q_, None, f_, st)
+        g_c = grad_color(color) if grad_color is not None else gc
+        dgr.backward_raw(g_c, gb, raw["xyz"], scene.shs, None, s_, q_, None, f_, radii, st, state,
+                         grads=holder["step"].buckets.raster, phase="blend")
+        stats["R"], stats["radii"] = state.num_rendered, radii
+        return {"v": v, "st": st, "s": s_, "q": q_, "f": f_, "radii": radii, "observe": observe, "state": state}
+
+    def finish_view(h, buckets, accumulate, rows):
+        st = h["st"]
+        dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, h["s"], h["q"], None, h["f"], h["radii"], st, h["state"],
+                         grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows,
+                         densify_stats=holder["step"].stats.backward_args())
+        buckets.chain_rows(raw, st.viewmatrix, st.campos, h["radii"], rows[0], rows[1], blend_metallic=blend_metallic)
+
+    def make_step(begin, world_=world, rank_=rank, n_streams=args.streams, buckets=None):
+        return vp.ViewShardedStep(P, M, device, world=world_, rank=rank_, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
+                                  begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets)
+
+    step = holder["step"] = make_step(begin_view)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
+
+    def timed(step_, steps):
+        holder["step"] = step_
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            step_.run(n_views)
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), wall
 
     for _ in range(args.warmup):
         step.run(n_views)
@@ -141,32 +183,22 @@ def run_ours(args, cfg, rank, world, device):
     clocks = ClockSampler(device.index)
     if rank == 0:
         clocks.start()
-    # ---- timed region 1: device-resident inputs ----
+    # ---- timed region 1 (headline): device-resident inputs ----
     launches0 = lib.gs2m_launch_count()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step.run(n_views)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    total_ms, _ = timed(step, args.steps)
     launches = torch.tensor([lib.gs2m_launch_count() - launches0], device=device, dtype=torch.int64)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    total_ms = float(ms[0])
     value = n_views * args.steps / (total_ms * 1e-3)
 
-    # ---- per-kernel device times: same step again with the library's cudaEvent brackets switched on (they sit on the
-    # launching stream around every stage; kept out of the region above so that event bookkeeping cannot perturb it)
-    # (single stream: with several views in flight the brackets of one stream would also span the other stream's kernels)
-    step_prof = vp.ViewShardedStep(P, M, device, render_view, world=world, rank=rank, n_streams=1)
-    step_prof.bucket_sets[0] = step_prof.buckets = step.buckets
+    # ---- per-kernel device times: the same step with the library's cudaEvent brackets switched on (they sit on the
+    # launching stream around every stage; kept out of the region above so that event bookkeeping cannot perturb it;
+    # single stream: with several views in flight the brackets of one stream would also span the other stream's kernels)
+    step_prof = holder["step"] = make_step(begin_view, world_=1, rank_=0, n_streams=1, buckets=step.buckets)
+    prof_views = my_views[:min(len(my_views), 4)]
     lib.gs2m_profile_enable(1)
     _native.profile_read()
-    for _ in range(max(1, min(args.steps, 2))):
-        step_prof.run(n_views, reduce=False)
+    step_prof._run_deferred(prof_views, reduce=False)
     torch.cuda.synchronize(device)
     stage = _native.profile_read()
     lib.gs2m_profile_enable(0)
@@ -186,104 +218,169 @@ def run_ours(args, cfg, rank, world, device):
     h_loss = torch.zeros(len(my_views), dtype=torch.float32).pin_memory()
     bg = torch.zeros(3, device=device)
     copy_stream = torch.cuda.Stream(device=device)
+    # every view of the step keeps its camera slot until its per-Gaussian stage has run (deferred): one slot per view
     slots = [dict(gt=torch.empty((3, H, W), device=device), wvt=torch.empty((4, 4), device=device),
                   full=torch.empty((4, 4), device=device), cpos=torch.empty(3, device=device),
-                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2 * max(args.streams, 1))]
+                  ready=torch.cuda.Event()) for _ in range(len(my_views))]
     h2d = sum(t.numel() * 4 for t in h_cam[my_views[0]]) + h_gt.numel() * 4
     d2h = 4
-    seq = {"k": 0}
-
     n_ahead = max(args.streams, 1)        # views in flight (one per stream); each view prefetches the one n_ahead later
+    step_done = torch.cuda.Event()
 
-    def prefetch(k, v):
-        sl = slots[k % len(slots)]
+    def prefetch(pos):
+        sl, v = slots[pos], my_views[pos]
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(sl["free"])
             sl["gt"].copy_(h_gt, non_blocking=True)
             sl["wvt"].copy_(h_cam[v][0], non_blocking=True)
             sl["full"].copy_(h_cam[v][1], non_blocking=True)
             sl["cpos"].copy_(h_cam[v][2], non_blocking=True)
             sl["ready"].record(copy_stream)
 
-    def render_view_e2e(v, buckets, accumulate):
-        k = seq["k"]
+    def begin_view_e2e(v):
         pos = my_views.index(v)
-        if k == 0:
-            for j in range(n_ahead):
-                prefetch(j, my_views[(pos + j) % len(my_views)])
-        prefetch(k + n_ahead, my_views[(pos + n_ahead) % len(my_views)])
-        sl = slots[k % len(slots)]
+        if pos == 0:
+            copy_stream.wait_event(step_done)      # the previous step's per-Gaussian stage has read every slot
+            for j in range(min(n_ahead, len(my_views))):
+                prefetch(j)
+        if pos + n_ahead < len(my_views):
+            prefetch(pos + n_ahead)
+        sl = slots[pos]
         torch.cuda.current_stream(device).wait_event(sl["ready"])
         st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, sl["wvt"],
                                                sl["full"], 3, sl["cpos"], False, F)
-        color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
-                                                               scene.scales, scene.rotations, None, feats[v], st)
-        diff = color - sl["gt"]
-        h_loss[pos].copy_((diff * diff).mean(), non_blocking=True)
-        grad_c = diff * (2.0 / diff.numel())
-        dgr.backward_raw(grad_c, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v],
-                         radii, st, state, grads=buckets.tensors, accumulate=accumulate,
-                         densify_stats=holder["e2e"].stats.backward_args())
-        sl["free"].record(torch.cuda.current_stream(device))
-        seq["k"] = k + 1
-        return {"radii": radii, "observe": observe}
 
-    step_e2e = holder["e2e"] = vp.ViewShardedStep(P, M, device, render_view_e2e, world=world, rank=rank, n_streams=args.streams)
-    step_e2e.bucket_sets, step_e2e.buckets = step.bucket_sets, step.buckets      # share the gradient buckets of the resident leg
-    step_e2e.run(n_views)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e.run(n_views)
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = n_views * args.steps / (float(ms2[0]) * 1e-3)
+        def grad_color(color):
+            diff = color - sl["gt"]
+            h_loss[pos].copy_((diff * diff).mean(), non_blocking=True)
+            return diff * (2.0 / diff.numel())
+        return begin_view(v, grad_color=grad_color, st=st)
+
+    step_e2e = make_step(begin_view_e2e, buckets=step.buckets)
+    step_done.record(torch.cuda.current_stream(device))
+
+    def run_e2e(steps):
+        holder["step"] = step_e2e
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            step_e2e.run(n_views)
+            step_done.record(torch.cuda.current_stream(device))
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), wall
+
+    run_e2e(1)
+    e2e_ms, wall_ms = run_e2e(args.steps)
+    e2e_value = n_views * args.steps / (e2e_ms * 1e-3)
     clock_info = clocks.stop() if rank == 0 else None
 
-    # ---- informative third leg: the training-faithful chain of SURVEY.md section 8e.  The features and the activated
-    # scale / rotation / opacity depend on the camera, so every view runs  fused packing forward -> rasterizer forward ->
-    # rasterizer backward (accumulate mode 2) -> fused packing backward (+=)  and the all-reduce covers the 64 floats per
-    # Gaussian of the nine raw parameter groups instead of the 73 of the rasterizer's inputs.  Reported as `param_chain`;
-    # the headline legs above are the north_star path (rasterizer forward+backward on given inputs).
-    from diff_gaussian_rasterization.packing import activate_and_pack
-    raw = syn.raw_parameters(scene)
-    order = ("xyz", "scaling", "rotation", "opacity", "albedo", "roughness", "metallic")
-
-    def render_view_params(v, buckets, accumulate):
-        st, cam = settings[v], cams[v]
-        with torch.no_grad():
-            s_, q_, o_, f_ = activate_and_pack(*[raw[k] for k in order], cam.world_view_transform, cam.camera_center,
-                                               blend_metallic=True)
-        color, radii, observe, buffer, state = dgr.forward_raw(raw["xyz"], scene.shs, None, o_, s_, q_, None, f_, st)
-        dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, s_, q_, None, f_, radii, st, state, grads=buckets.raster,
-                         accumulate=buckets.raster_accumulate_mode(accumulate),
-                         densify_stats=holder["params"].stats.backward_args())
-        buckets.chain_view(raw, cam.world_view_transform, cam.camera_center, radii, blend_metallic=True)
-        return {"radii": radii, "observe": observe}
-
-    step.bucket_sets = step_e2e.bucket_sets = None          # release the 73-float buckets before allocating the 64-float ones
-    step.buckets = step_e2e.buckets = step_prof.buckets = None
-    step_prof.bucket_sets = None
-    step_p = holder["params"] = vp.ViewShardedStep(P, M, device, render_view_params, world=world, rank=rank,
-                                                   n_streams=args.streams, buckets_cls=vp.ParameterBuckets)
-    for _ in range(2):
-        step_p.run(n_views)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_p.run(n_views)
-    e1.record()
-    barrier()
-    ms3 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
+    # ---- data-parallel correctness, outside the timed regions (N > 1): after one step every rank must hold the gradient of
+    # the WHOLE batch, i.e. what a single rank gets by running all world*V views one after the other, and all ranks must
+    # hold identical bits ----
+    dp_check = None
     if world > 1:
-        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
-    param_chain_value = n_views * args.steps / (float(ms3[0]) * 1e-3)
-    param_chain_bytes = step_p.buckets.nbytes_reduced()
+        holder["step"] = step
+        step.run(n_views)
+        torch.cuda.synchronize(device)
+        got = {k: t.clone() for k, t in step.buckets.tensors.items()}
+        seq_step = holder["step"] = make_step(begin_view, world_=1, rank_=0, n_streams=1, buckets=step.buckets)
+        seq_step.run(n_views, reduce=False)
+        torch.cuda.synchronize(device)
+        errs = {}
+        for k in vp.ParameterBuckets.names:
+            d = (got[k].double() - step.buckets.tensors[k].double()).abs().max()
+            errs[k] = float(d / step.buckets.tensors[k].double().abs().max().clamp_min(1e-30))
+        checksum = torch.stack([t.view(torch.int32).to(torch.int64).sum() for t in got.values()]).sum().reshape(1)
+        sums = [torch.zeros_like(checksum) for _ in range(world)]
+        dist.all_gather(sums, checksum)
+        worst = torch.tensor([max(v for k, v in errs.items() if k not in ("scaling", "rotation")),
+                              max(errs["scaling"], errs["rotation"])], device=device, dtype=torch.float64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        identical = all(int(x) == int(sums[0]) for x in sums)
+        dp_check = {"views": n_views, "max_rel_err_vs_sequential_sum": float(worst[0]),
+                    "max_rel_err_ill_conditioned(scaling,rotation)": float(worst[1]),
+                    "ranks_bit_identical": identical,
+                    "pass": bool(float(worst[0]) <= 1e-4 and float(worst[1]) <= 2e-3 and identical),
+                    "what": "all-reduced raw-parameter gradients of one step on every rank vs the same rank running all %d views "
+                            "sequentially (max|d|/max|ref| per group, max over groups and ranks; 1e-4, and 2e-3 for the "
+                            "ill-conditioned scaling/rotation pair whose single-GPU run-to-run noise is ~3e-4)" % n_views}
+        del got
+        if not dp_check["pass"] and rank == 0:
+            print("dp_check FAILED: %s" % json.dumps(dp_check), file=sys.stderr)
+
+    # ---- side leg: the rasterizer alone on given inputs (the reference arm's workload; round 1's headline): forward +
+    # backward per view into the gradients of the rasterizer's own inputs (73 floats per Gaussian), same deferred step ----
+    param_bytes = step.buckets.nbytes_reduced()
+    step.bucket_sets = step_e2e.bucket_sets = step_prof.bucket_sets = None
+    step.buckets = step_e2e.buckets = step_prof.buckets = None
+    holder["step"] = None
+    torch.cuda.empty_cache()
+    feats = {v: syn.pack_features(scene, cams[v], F) for v in my_views}
+
+    def begin_raster(v):
+        st = settings[v]
+        color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities, scene.scales,
+                                                               scene.rotations, None, feats[v], st)
+        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], radii, st,
+                         state, grads=holder["step"].buckets.tensors, phase="blend")
+        return {"v": v, "radii": radii, "observe": observe, "state": state}
+
+    def finish_raster(h, buckets, accumulate, rows):
+        v = h["v"]
+        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], h["radii"],
+                         settings[v], h["state"], grads=buckets.tensors, accumulate=accumulate, phase="gaussians", rows=rows,
+                         densify_stats=holder["step"].stats.backward_args())
+
+    step_r = vp.ViewShardedStep(P, M, device, world=world, rank=rank, n_streams=args.streams, begin_view=begin_raster,
+                                finish_view=finish_raster, n_chunks=args.chunks)
+    holder["step"] = step_r
+    for _ in range(2):
+        step_r.run(n_views)
+    raster_ms, _ = timed(step_r, args.steps)
+    raster_value = n_views * args.steps / (raster_ms * 1e-3)
+    raster_bytes = step_r.buckets.nbytes_reduced()
+
+    # ---- side leg (N = 1): what an unmodified GS-2M iteration sees — the drop-in autograd API on ONE stream, two views per
+    # iteration with the gradients accumulating in the leaves' .grad (train.py:95, utils/loss_utils.py:253) ----
+    dropin = None
+    if world == 1:
+        step_r.bucket_sets = step_r.buckets = None
+        torch.cuda.empty_cache()
+        leaves = dict(means3D=scene.means3D.clone().requires_grad_(True), opacities=scene.opacities.clone().requires_grad_(True),
+                      shs=scene.shs.clone().requires_grad_(True), scales=scene.scales.clone().requires_grad_(True),
+                      rotations=scene.rotations.clone().requires_grad_(True))
+        m2d = torch.zeros(P, 4, device=device, requires_grad=True)
+        fl = {v: feats[v].clone().requires_grad_(True) for v in my_views[:2]}
+
+        def iteration():
+            for v in my_views[:2]:
+                color, radii, observe, buffer = dgr.GaussianRasterizer(settings[v])(
+                    means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"], colors_precomp=None,
+                    scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None, features=fl[v])
+                torch.autograd.backward([color, buffer], [gc, gb])
+        for _ in range(2):
+            iteration()
+        torch.cuda.synchronize(device)
+        n_it = max(2, args.steps * V_per // 4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_it):
+            iteration()
+        e1.record()
+        torch.cuda.synchronize(device)
+        d_ms, d_wall = e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3
+        n_v = 2 * n_it
+        dropin = {"value": round(n_v / (d_ms * 1e-3), 3), "unit": UNIT, "ms_per_view": round(d_ms / n_v, 4),
+                  "wall_ms_per_view": round(d_wall / n_v, 4),
+                  "what": "GaussianRasterizer(settings)(...) + torch.autograd.backward on torch's current stream, 2 views per "
+                          "iteration, .grad accumulation by autograd (rasterizer only, like the reference arm)"}
 
     if rank != 0:
         return None
@@ -295,6 +392,7 @@ def run_ours(args, cfg, rank, world, device):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_prof = max(len(prof_views), 1)
     bwd_ms, bwd_calls = stage["blend_bwd"]
     bwd_avg_ms = bwd_ms / max(bwd_calls, 1)
     achieved = ab["blend_bwd"] / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
@@ -304,21 +402,26 @@ def run_ours(args, cfg, rank, world, device):
     except Exception:
         pass
     per_view_ms = total_ms / (args.steps * V_per)
+    raster_view_ms = raster_ms / (args.steps * V_per)
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d Gaussians, %dx%d, SH deg 3, feature_count %d (RGB+alpha+depth+normal+albedo+"
-                               "roughness+metallic), fwd+bwd, %d views per rank per step, view-sharded DP + NCCL all-reduce"
+                               "roughness+metallic), %d views per rank per step; per view: fused activation+packing fwd, rasterizer "
+                               "fwd+bwd, fused packing bwd into the 9 raw parameter-gradient groups (64 floats/Gaussian); "
+                               "view-sharded DP, NCCL all-reduce of the parameter gradients overlapped range by range"
                                % (args.config, P, W, H, F, V_per),
-                   "views_per_step": n_views, "streams_per_rank": step.n_streams, "visible_gaussians": V_vis, "instances_R": R,
+                   "views_per_step": n_views, "streams_per_rank": step.n_streams, "gaussian_ranges": len(step.chunks),
+                   "allreduce_bytes": param_bytes, "visible_gaussians": V_vis, "instances_R": R,
                    "l2_policy": "working set per view (%.1f GB algorithmic) exceeds the 126 MB L2; no flush needed"
                                 % (ab["total"] / 1e9)},
         "ms_per_view": round(per_view_ms, 4),
         "gpu_launches": int(launches[0]),
-        "param_chain": {"value": round(param_chain_value, 3), "unit": UNIT, "allreduce_bytes": param_chain_bytes,
-                        "what": "per view: fused activation+packing fwd, rasterizer fwd+bwd, fused packing bwd (+=); "
-                                "all-reduce of the 9 raw parameter-gradient groups"},
+        "raster_only": {"value": round(raster_value, 3), "unit": UNIT, "ms_per_view": round(raster_view_ms, 4),
+                        "allreduce_bytes": raster_bytes,
+                        "what": "rasterizer forward+backward alone on given inputs (the reference arm's workload): gradients of "
+                                "the rasterizer's own inputs, 73 floats/Gaussian, same deferred view-sharded step"},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d * V_per, "d2h_bytes_per_step": d2h * V_per,
                 "wall_ms_per_step": round(wall_ms / args.steps, 4)},
         "roofline": {"bound": "hbm", "kernel": "blend_backward_kernel<%d>" % F, "achieved": round(achieved, 2),
@@ -326,11 +429,17 @@ def run_ours(args, cfg, rank, world, device):
                      "algorithmic_bytes_per_launch": ab["blend_bwd"], "avg_launch_ms": round(bwd_avg_ms, 4),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "note": "blend kernels are FP32-issue/shared-memory bound, not HBM bound (DESIGN.md)"},
-        "roofline_view": {"algorithmic_bytes_per_view": ab["total"], "achieved": round(ab["total"] / (per_view_ms * 1e-3) / 1e9, 2),
-                          "frac": round(ab["total"] / (per_view_ms * 1e-3) / 1e9 / peak, 5), "unit": "GB/s"},
-        "stage_ms_per_view": {k: round(v[0] / max(v[1], 1), 4) for k, v in stage.items()},
+        "roofline_view": {"algorithmic_bytes_per_view": ab["total"],
+                          "achieved": round(ab["total"] / (raster_view_ms * 1e-3) / 1e9, 2),
+                          "frac": round(ab["total"] / (raster_view_ms * 1e-3) / 1e9 / peak, 5), "unit": "GB/s",
+                          "note": "rasterizer-only leg (the byte model of SURVEY 8d covers the rasterizer's stages)"},
+        "stage_ms_per_view": {k: round(v[0] / n_prof, 4) for k, v in stage.items()},
         "clocks": clock_info,
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    if dropin is not None:
+        line["dropin"] = dropin
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, args)
     return line
@@ -429,7 +538,7 @@ def run_reference(args, cfg, rank, world, device):
     torch.cuda.synchronize(device)
     total_ms = e0.elapsed_time(e1)
     value = V_per * args.steps / (total_ms * 1e-3)
-    return {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world,
+    return {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: %d Gaussians, %dx%d, feature_count %d, fwd+bwd, %d views per step on ONE GPU "
@@ -450,7 +559,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="tnt-3m", choices=sorted(syn.CONFIGS))
     ap.add_argument("--views-per-rank", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=2, help="views in flight per rank (CUDA streams) in the resident leg")
+    ap.add_argument("--streams", type=int, default=2, help="views in flight per rank (CUDA streams)")
+    ap.add_argument("--chunks", type=int, default=4, help="Gaussian ranges of the deferred per-Gaussian backward / all-reduce")
     ap.add_argument("--cpu-tiles", type=int, default=96, help="tiles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -382,6 +382,12 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     }
     if (a->R < 0) { set_error("backward: negative R"); return GS2M_ERR_INVALID_ARGUMENT; }
     if (a->accumulate < 0 || a->accumulate > 2) { set_error("backward: accumulate mode %d outside 0..2", a->accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
+    if (a->phase < 0 || a->phase > 2) { set_error("backward: phase %d outside 0..2", a->phase); return GS2M_ERR_INVALID_ARGUMENT; }
+    const bool ranged = a->row_end > 0 || a->row_begin != 0;
+    if (ranged && (a->phase != 2 || a->row_begin < 0 || a->row_end > a->P || a->row_begin > a->row_end || (a->row_begin & 255))) {
+        set_error("backward: rows [%d, %d) need phase 2, 0 <= begin <= end <= P and begin %% 256 == 0", a->row_begin, a->row_end);
+        return GS2M_ERR_INVALID_ARGUMENT;
+    }
     if (a->R_capacity < 0 || (a->R_capacity > 0 && a->R > a->R_capacity)) { set_error("backward: R %d does not fit R_capacity %d", a->R, a->R_capacity); return GS2M_ERR_INVALID_ARGUMENT; }
     const int R_carve = a->R_capacity > 0 ? a->R_capacity : a->R;    // what forward sized the binning arena for
     if (a->geometry_bytes < GeomState::carve(nullptr, a->P, nullptr) ||
@@ -406,6 +412,8 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     p.dL_dmeans2D = a->dL_dmeans2D; p.dL_dconic = a->dL_dconic; p.dL_dopacity = a->dL_dopacity; p.dL_dcolor = a->dL_dcolor;
     p.dL_dmeans3D = a->dL_dmeans3D; p.dL_dcov3D = a->dL_dcov3D; p.dL_dsh = a->dL_dsh; p.dL_dscale = a->dL_dscale;
     p.dL_drot = a->dL_drot; p.dL_dfeatures = a->dL_dfeatures; p.accumulate = a->accumulate;
+    p.row_begin = ranged ? a->row_begin : 0;
+    p.row_end = ranged ? a->row_end : a->P;
     p.densify_grad_accum = a->densify_grad_accum; p.densify_grad_accum_abs = a->densify_grad_accum_abs;
     p.densify_denom = a->densify_denom;
 
@@ -419,10 +427,15 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
 
     // The accumulator rows of the visible Gaussians were zeroed by the forward (preprocess); a second backward over the same
     // forward state has to start from zero again.
-    if (a->grad_acc_dirty) GS2M_CUDA(cudaMemsetAsync(g.grad_acc, 0, (size_t)p.P * GS2M_ACC_STRIDE * sizeof(float), s));
-    { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, b.masks, im, s); }
-    if (rc != GS2M_OK) return rc;
-    { StageTimer t(GS2M_STAGE_PREPROCESS_BWD, s); rc = launch_preprocess_backward(p, g, s); }
+    if (a->phase != 2) {
+        if (a->grad_acc_dirty) GS2M_CUDA(cudaMemsetAsync(g.grad_acc, 0, (size_t)p.P * GS2M_ACC_STRIDE * sizeof(float), s));
+        { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, b.masks, im, s); }
+        if (rc != GS2M_OK) return rc;
+    }
+    if (a->phase != 1 && p.row_end > p.row_begin) {
+        StageTimer t(GS2M_STAGE_PREPROCESS_BWD, s);
+        rc = launch_preprocess_backward(p, g, s);
+    }
     return rc;
 }
 

@@ -130,6 +130,7 @@ struct BwdParams {
     float *dL_dmeans2D, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscale, *dL_drot,
           *dL_dfeatures;
     int accumulate;
+    int row_begin, row_end;                                                // Gaussians the per-Gaussian stage covers
     float *densify_grad_accum, *densify_grad_accum_abs, *densify_denom;   // optional (nullptr = off)
 };
 int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,

@@ -410,8 +410,8 @@ __device__ __forceinline__ void block_store(float* __restrict__ dst, const float
 
 template <int MODE>
 __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdParams p, GeomState g) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+    const int idx = p.row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.row_end) return;
     GlobalIO<MODE> io(p, (size_t)idx);
     gaussian_backward(p, g, idx, p.radii[idx] > 0, io);
 }
@@ -422,8 +422,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StageSmem& sm = *reinterpret_cast<StageSmem*>(smem_raw);
     const int t = threadIdx.x;
-    const size_t row0 = (size_t)blockIdx.x * 256;
-    const int rows = (int)min((size_t)256, (size_t)p.P - row0);
+    const size_t row0 = (size_t)p.row_begin + (size_t)blockIdx.x * 256;      // row_begin is a multiple of 256 (checked by the API)
+    const int rows = (int)min((size_t)256, (size_t)p.row_end - row0);
     const int idx = (int)row0 + t;
     const bool inside = t < rows;
     const bool visible = inside && p.radii[idx] > 0;
@@ -488,8 +488,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
 }  // namespace
 
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
-    if (p.P == 0) return GS2M_OK;
-    const int blocks = (p.P + 255) / 256;
+    if (p.P == 0 || p.row_end <= p.row_begin) return GS2M_OK;
+    const int blocks = (p.row_end - p.row_begin + 255) / 256;
     count_launches(1);
     if (p.accumulate < 0 || p.accumulate > 2) { set_error("accumulate mode %d outside 0..2", p.accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
     if (p.M <= 16) {

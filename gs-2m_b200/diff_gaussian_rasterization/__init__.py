@@ -217,12 +217,15 @@ def alloc_grads(P, M, device, zero=False):
 
 def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features,
                  radii, raster_settings: GaussianRasterizationSettings, state: RasterState, grads=None,
-                 accumulate=False, densify_stats=None):
+                 accumulate=False, densify_stats=None, phase="all", rows=None):
     """Run the backward pipeline into ``grads`` (dict from :func:`alloc_grads`; allocated when None).
     With ``accumulate=True`` (or 1) the nine caller-visible tensors are updated with ``+=``; with ``accumulate=2`` only
     ``dL_dmeans3D`` and ``dL_dsh`` (GS-2M's raw, view-independent parameters) are, the rest is overwritten.
     ``densify_stats = (xyz_gradient_accum, xyz_gradient_accum_abs, denom)`` (float ``[P]`` / ``[P,1]`` CUDA tensors, any may be
-    None) are updated like ``GaussianModel.add_densification_stats`` with this view's screen-space gradient."""
+    None) are updated like ``GaussianModel.add_densification_stats`` with this view's screen-space gradient.
+    ``phase``: "all" (default), "blend" (only the reverse blend, which fills the state's internal accumulator) or "gaussians"
+    (only the per-Gaussian stage, for Gaussians ``rows = (begin, end)`` when given; ``begin`` a multiple of 256) — a view-sharded
+    step runs "blend" per view and defers "gaussians" range by range so that finished ranges can be all-reduced early."""
     lib = _native.load()
     dev = means3D.device
     rs = raster_settings
@@ -263,8 +266,12 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
     with torch.cuda.device(dev):
         b = _native.BackwardArgs()
         b.P, b.D, b.M, b.R, b.R_capacity = P, int(rs.sh_degree), M, int(state.num_rendered), int(state.capacity)
-        b.grad_acc_dirty = int(state.backward_runs > 0 or not state.prepared)
-        state.backward_runs += 1
+        b.phase = {"all": 0, "blend": 1, "gaussians": 2}[phase]
+        if rows is not None:
+            b.row_begin, b.row_end = int(rows[0]), int(rows[1])
+        if phase != "gaussians":
+            b.grad_acc_dirty = int(state.backward_runs > 0 or not state.prepared)
+            state.backward_runs += 1
         b.background = _ptr(bg)
         b.width, b.height = W, H
         b.means3D, b.shs, b.colors_precomp, b.scales = _ptr(means3D), _ptr(shs_t), _ptr(col_t), _ptr(sca_t)

@@ -58,6 +58,7 @@ class BackwardArgs(C.Structure):
         ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscale", _fp), ("dL_drot", _fp), ("dL_dfeatures", _fp),
         ("accumulate", C.c_int),
         ("stream", C.c_void_p),
+        ("phase", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int),
         ("grad_acc_dirty", C.c_int),
         ("densify_grad_accum", _fp), ("densify_grad_accum_abs", _fp), ("densify_denom", _fp),
     ]

@@ -12,9 +12,12 @@ module does the same sum across a *batch* of views and across ranks:
   the batch gradient.
 * ``DensificationStats``                 – GS-2M's densification bookkeeping (max_radii2D, xyz_gradient_accum{,_abs}, denom,
   observe_cnt; train.py:225-245, scene/gaussian_model.py:569-573) with fused per-view updates, MAX / SUM all-reduced.
-* ``ViewShardedStep``                    – runs forward+backward for this rank's views through a caller-supplied
-  ``render_view`` callable and finishes with the all-reduce.  The callable is the only piece that touches CUDA, so
-  the sharding / accumulation / reduction logic is testable on CPU with the gloo backend.
+* ``ViewShardedStep``                    – runs forward+backward for this rank's views through caller-supplied callables and
+  reduces the gradients over the ranks.  The callables are the only pieces that touch CUDA, so the sharding / accumulation /
+  reduction logic is testable on CPU with the gloo backend.  Two protocols: ``render_view`` (a view's whole forward+backward
+  in one call; one all-reduce at the end of the step) and ``begin_view`` / ``finish_view`` (the *deferred* step: a view's
+  forward and reverse blend run as soon as possible, the per-Gaussian half of every view's backward runs afterwards, Gaussian
+  range by Gaussian range, and the all-reduce of a finished range overlaps the next range's kernels).
 
 One process per GPU (torchrun); the path shards with no data-path collective other than this one exchange step.
 """
@@ -41,6 +44,49 @@ def shard_views(n_views: int, world: int, rank: int) -> range:
 
 def _dist_ready() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _row_chunks(P: int, n_chunks: int):
+    """[(begin, end)] splitting P rows into about n_chunks ranges whose starts are multiples of 256 (the per-Gaussian backward's
+    block size)."""
+    if P <= 0:
+        return []
+    per = -(-P // max(n_chunks, 1))
+    per = max(256, -(-per // 256) * 256)
+    return [(b, min(b + per, P)) for b in range(0, P, per)]
+
+
+def _record_stream(obj, stream):
+    """Tell the caching allocator that the tensors of a view handle (dict values, and the arenas of a rasterizer state) are
+    also used on `stream`, so that freeing them does not hand their memory out while that stream still reads it."""
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream)
+    else:
+        for name in ("geom", "binning", "img"):
+            t = getattr(obj, name, None)
+            if isinstance(t, torch.Tensor):
+                _record_stream(t, stream)
+
+
+def _all_reduce_many(tensors, async_op):
+    """SUM all-reduce of several tensors as ONE collective launch where the backend can coalesce them (NCCL group call)."""
+    if not tensors:
+        return []
+    try:
+        with dist._coalescing_manager(async_ops=async_op) as cm:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [cm] if async_op else []
+    except (AttributeError, RuntimeError, ValueError):
+        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op) for t in tensors]
+        return works if async_op else []
 
 
 class GradientBuckets:
@@ -86,6 +132,19 @@ class GradientBuckets:
             return []
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return [work] if async_op else []
+
+    def all_reduce_rows(self, begin: int, end: int, async_op: bool = True):
+        """SUM over ranks of the Gaussians [begin, end) of every reduced tensor (one coalesced collective)."""
+        if not _dist_ready() or end <= begin:
+            return []
+        return _all_reduce_many([self.tensors[n][begin:end] for n in self.names], async_op)
+
+    def begin_rows(self):
+        """Called once per step before the deferred per-Gaussian stage (nothing to prepare: the first view overwrites)."""
+
+    def zero_rows(self, begin: int, end: int):
+        for n in self.names:
+            self.tensors[n][begin:end].zero_()
 
 
 class ParameterBuckets:
@@ -157,6 +216,33 @@ class ParameterBuckets:
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return [work] if async_op else []
 
+    def all_reduce_rows(self, begin: int, end: int, async_op: bool = True):
+        if not _dist_ready() or end <= begin:
+            return []
+        return _all_reduce_many([self.tensors[n][begin:end] for n in self.names], async_op)
+
+    def begin_rows(self):
+        """Deferred step: the groups ``chain_view`` adds into start the step at zero (``xyz`` / ``sh`` are overwritten by the
+        first view's rasterizer backward)."""
+        self.flat[self._packed_from:].zero_()
+
+    def zero_rows(self, begin: int, end: int):
+        for n in self.names:
+            self.tensors[n][begin:end].zero_()
+
+    def chain_rows(self, raw: Dict[str, torch.Tensor], world_view_transform, camera_center, radii, begin: int, end: int,
+                   z_depth=False, blend_metallic=False):
+        """``chain_view`` for the Gaussians [begin, end) only (the packing backward is per Gaussian: row slices of every
+        operand)."""
+        from diff_gaussian_rasterization import packing
+        t, r = self.tensors, self.raster
+        sl = slice(begin, end)
+        packing.pack_backward_accumulate(
+            raw["xyz"][sl], raw["scaling"][sl], raw["rotation"][sl], raw["opacity"][sl], raw["albedo"][sl], raw["roughness"][sl],
+            raw["metallic"][sl], world_view_transform, camera_center, r["dL_dscale"][sl], r["dL_drot"][sl], r["dL_dopacity"][sl],
+            r["dL_dfeatures"][sl], t["xyz"][sl], t["scaling"][sl], t["rotation"][sl], t["opacity"][sl], t["albedo"][sl],
+            t["roughness"][sl], t["metallic"][sl], radii[sl], z_depth=z_depth, blend_metallic=blend_metallic)
+
 
 class DensificationStats:
     """GS-2M's densification bookkeeping for one step, reference semantics and dtypes (float tensors):
@@ -227,15 +313,25 @@ class ViewShardedStep:
     read-back or in a tail wave; the bucket sets are summed once per step before the all-reduce.
     """
 
-    def __init__(self, P: int, M: int, device, render_view: Callable[[int, GradientBuckets, bool], Optional[dict]],
-                 world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1, buckets_cls=None):
+    def __init__(self, P: int, M: int, device, render_view: Optional[Callable[[int, GradientBuckets, bool], Optional[dict]]] = None,
+                 world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1, buckets_cls=None,
+                 begin_view: Optional[Callable[[int], dict]] = None,
+                 finish_view: Optional[Callable[[dict, object, bool, tuple], None]] = None, n_chunks: int = 4, buckets=None):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
         self.device = torch.device(device)
         use_streams = n_streams > 1 and self.device.type == "cuda"
         self.n_streams = n_streams if use_streams else 1
+        self.deferred = begin_view is not None
+        if self.deferred == (render_view is not None) or (self.deferred and finish_view is None):
+            raise ValueError("give either render_view, or begin_view together with finish_view")
+        self.begin_view, self.finish_view, self.P = begin_view, finish_view, P
+        self.chunks = _row_chunks(P, n_chunks)
         buckets_cls = buckets_cls or GradientBuckets        # ParameterBuckets: raw-parameter gradients, chained per view
-        self.bucket_sets = [buckets_cls(P, M, device) for _ in range(self.n_streams)]
+        # the deferred step sums all of a rank's views in ONE bucket set (its per-Gaussian stage runs on one stream)
+        # (`buckets`: an existing bucket set to accumulate into instead of allocating one)
+        n_sets = 1 if self.deferred else self.n_streams
+        self.bucket_sets = [buckets] if (buckets is not None and n_sets == 1) else [buckets_cls(P, M, device) for _ in range(n_sets)]
         self.buckets = self.bucket_sets[0]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams)] if use_streams else [None]
         self.render_view = render_view
@@ -251,9 +347,59 @@ class ViewShardedStep:
             if "means2D_grad" in out:
                 self.stats.update_backward_eager(out["means2D_grad"], out["radii"])
 
+    def _run_deferred(self, mine: List[int], reduce: bool) -> Dict[str, torch.Tensor]:
+        """Phase A: every view's forward + reverse blend (``begin_view``), round-robin over the streams.  Phase B: the
+        per-Gaussian stage of every view (``finish_view(handle, buckets, accumulate, (begin, end))``), Gaussian range by
+        Gaussian range on the main stream; as soon as a range has received all of the rank's views its all-reduce is queued
+        (NCCL's own stream), so it runs under the next range's kernels and only the last range's exchange is exposed."""
+        cuda = self.device.type == "cuda"
+        handles = []
+        if cuda and self.n_streams > 1 and mine:
+            main = torch.cuda.current_stream(self.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for k, v in enumerate(mine):
+                j = k % self.n_streams
+                with torch.cuda.stream(self.streams[j]):
+                    if k < self.n_streams:
+                        self.streams[j].wait_event(ready)
+                    handles.append(self._begin(v))
+            for j in range(min(self.n_streams, len(mine))):
+                main.wait_stream(self.streams[j])
+            for h in handles:                                     # allocated on a side stream, consumed on the main one
+                _record_stream(h, main)
+        else:
+            handles = [self._begin(v) for v in mine]
+        self.buckets.begin_rows()
+        works = []
+        for (b, e) in self.chunks:
+            if not handles:
+                self.buckets.zero_rows(b, e)                      # more ranks than views: contribute zeros
+            for k, h in enumerate(handles):
+                self.finish_view(h, self.buckets, k > 0, (b, e))
+            if reduce:
+                works += self.buckets.all_reduce_rows(b, e, async_op=True)
+        for w in works:
+            w.wait()                                              # stream-level wait: later work sees the reduced gradients
+        if cuda and self.n_streams > 1 and mine:
+            for j in range(min(self.n_streams, len(mine))):       # the side streams' next step must wait for this one
+                self.streams[j].wait_stream(main)
+        self.buckets.views_accumulated = len(mine)
+        if reduce:
+            self.stats.all_reduce()
+        return self.buckets.tensors
+
+    def _begin(self, v):
+        h = self.begin_view(v)
+        if h and "radii" in h and "observe" in h:
+            self.stats.update_forward(h["radii"], h["observe"])
+        return h
+
     def run(self, n_views: int, reduce: bool = True) -> Dict[str, torch.Tensor]:
         mine = self.local_views(n_views)
         self.stats.zero_()
+        if self.deferred:
+            return self._run_deferred(mine, reduce)
         if not mine:  # more ranks than views: contribute zeros
             self.buckets.zero_()
         if self.n_streams == 1:

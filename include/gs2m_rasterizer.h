@@ -147,6 +147,13 @@ typedef struct gs2m_backward_args {
     float* dL_dfeatures;        /* [P,10] */
     int accumulate;
     void* stream;
+    /* The backward has two stages: the reverse blend over the tile lists (fills an internal per-Gaussian accumulator in the
+     * geometry arena) and the per-Gaussian stage (accumulator -> the ten gradient tensors).  phase 0 runs both; phase 1 only the
+     * blend; phase 2 only the per-Gaussian stage, restricted to Gaussians [row_begin, row_end) when row_end > 0 (row_begin must
+     * be a multiple of 256).  A view-sharded step runs phase 1 per view as soon as the view is rendered and defers phase 2,
+     * range by range over all of its views, so that the all-reduce of a finished range overlaps the next range's work. */
+    int phase;
+    int row_begin, row_end;
     int grad_acc_dirty;         /* 0 for the first backward after a forward (which zeroed the internal accumulator rows of the
                                    visible Gaussians); 1 when backward runs again over the same forward state, or when the
                                    forward ran with no_backward: the library then clears the accumulator first */

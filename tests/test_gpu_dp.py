@@ -29,6 +29,20 @@ def _make_render(dgr, scene, cams, feats, gc, gb):
                          settings[v], state, grads=buckets.tensors, accumulate=accumulate,
                          densify_stats=holder["step"].stats.backward_args())
         return {"radii": radii, "observe": observe}
+
+    def begin_view(v):          # deferred protocol (same arithmetic, the per-Gaussian stage postponed and split into ranges)
+        color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities,
+                                                               scene.scales, scene.rotations, None, feats[v], settings[v])
+        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], radii,
+                         settings[v], state, grads=holder["step"].buckets.tensors, phase="blend")
+        return {"v": v, "radii": radii, "observe": observe, "state": state}
+
+    def finish_view(h, buckets, accumulate, rows):
+        v = h["v"]
+        dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], h["radii"],
+                         settings[v], h["state"], grads=buckets.tensors, accumulate=accumulate, phase="gaussians", rows=rows,
+                         densify_stats=holder["step"].stats.backward_args())
+    holder["deferred"] = (begin_view, finish_view)
     return render_view, holder
 
 
@@ -42,7 +56,7 @@ def _setup(device):
     return dgr, scene, cams, feats, gc.to(device), gb.to(device)
 
 
-def _worker(rank, world, port, out_dir, n_streams):
+def _worker(rank, world, port, out_dir, n_streams, deferred=False):
     import view_parallel as vp
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -52,7 +66,11 @@ def _worker(rank, world, port, out_dir, n_streams):
     try:
         dgr, scene, cams, feats, gc, gb = _setup(device)
         render, holder = _make_render(dgr, scene, cams, feats, gc, gb)
-        step = holder["step"] = vp.ViewShardedStep(P, 16, device, render, n_streams=n_streams)
+        if deferred:
+            step = holder["step"] = vp.ViewShardedStep(P, 16, device, n_streams=n_streams, begin_view=holder["deferred"][0],
+                                                       finish_view=holder["deferred"][1], n_chunks=3)
+        else:
+            step = holder["step"] = vp.ViewShardedStep(P, 16, device, render, n_streams=n_streams)
         for t in step.buckets.tensors.values():
             t.fill_(7.0)                                    # stale content must not leak into the step
         grads = step.run(N_VIEWS)
@@ -71,13 +89,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("n_streams", [1, 2])
-def test_two_gpu_step_equals_single_gpu_sequential_sum(tmp_path, n_streams):
+@pytest.mark.parametrize("n_streams,deferred", [(1, False), (2, False), (2, True)])
+def test_two_gpu_step_equals_single_gpu_sequential_sum(tmp_path, n_streams, deferred):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 CUDA devices")
     import view_parallel as vp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), n_streams), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), n_streams, deferred), nprocs=world, join=True)
     res = [torch.load(os.path.join(tmp_path, "rank%d.pt" % r)) for r in range(world)]
     # single-GPU sequential reference: the same four views, one after the other, on cuda:0
     device = torch.device("cuda", 0)

@@ -11,8 +11,8 @@ import view_parallel as vp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_streams", [1, 2])
-def test_parameter_step_matches_autograd_over_views(n_streams):
+@pytest.mark.parametrize("n_streams,deferred", [(1, False), (2, False), (1, True), (2, True)])
+def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization.packing import activate_and_pack
     P, W, H, F, M, n_views = 30_000, 320, 240, 10, 16, 4
@@ -49,7 +49,30 @@ def test_parameter_step_matches_autograd_over_views(n_streams):
         buckets.chain_view(raw, cam.world_view_transform, cam.camera_center, radii, blend_metallic=True)
         return {"radii": radii, "observe": observe}
 
-    step = vp.ViewShardedStep(P, M, "cuda", render_view, world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets)
+    # ---- the deferred step: forward + reverse blend per view, then the per-Gaussian stage + packing chain range by range ----
+    def begin_view(v):
+        cam, st = cams[v], settings[v]
+        with torch.no_grad():
+            s, q, o, f = activate_and_pack(*[raw[k] for k in order], cam.world_view_transform, cam.camera_center,
+                                           blend_metallic=True)
+        color, radii, observe, buffer, state = dgr.forward_raw(raw["xyz"], scene.shs, None, o, s, q, None, f, st)
+        h = dict(v=v, s=s, q=q, f=f, radii=radii, observe=observe, state=state)
+        dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, s, q, None, f, radii, st, state, grads=step.buckets.raster,
+                         phase="blend")
+        return h
+
+    def finish_view(h, buckets, accumulate, rows):
+        cam, st = cams[h["v"]], settings[h["v"]]
+        dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, h["s"], h["q"], None, h["f"], h["radii"], st, h["state"],
+                         grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows)
+        buckets.chain_rows(raw, cam.world_view_transform, cam.camera_center, h["radii"], rows[0], rows[1], blend_metallic=True)
+
+    if deferred:
+        step = vp.ViewShardedStep(P, M, "cuda", world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
+                                  begin_view=begin_view, finish_view=finish_view, n_chunks=5)
+        assert len(step.chunks) == 5 and len(step.bucket_sets) == 1
+    else:
+        step = vp.ViewShardedStep(P, M, "cuda", render_view, world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets)
     for b in step.bucket_sets:
         b.flat.fill_(3.0)                                   # stale content must not leak into the step
     got = step.run(n_views, reduce=False)
@@ -87,3 +110,31 @@ def test_accumulate_mode_2_overwrites_the_view_dependent_tensors():
         assert float(g[k][~vis].abs().max()) == 0.0, k      # ... with zeros for culled Gaussians
     with pytest.raises(dgr.RasterizerError):
         dgr.backward_raw(*args, grads=g, accumulate=3)
+
+
+def test_backward_phases_and_row_ranges_equal_the_whole_backward():
+    """phase="blend" followed by phase="gaussians" over 256-aligned row ranges writes exactly what the one-call backward writes
+    (the per-Gaussian stage is independent per Gaussian), in overwrite and in accumulate mode."""
+    import diff_gaussian_rasterization as dgr
+    P, W, H, F = 21_000, 256, 192, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.6)
+    st = syn.raster_settings_for(cam, F, dgr.GaussianRasterizationSettings)
+    color, radii, observe, buffer, state = dgr.forward_raw(scene.means3D, scene.shs, None, scene.opacities, scene.scales,
+                                                           scene.rotations, None, feats, st)
+    args = (gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats, radii, st, state)
+    whole = {k: v.clone() for k, v in dgr.backward_raw(*args).items()}
+    for acc in (0, 1):
+        g = dgr.alloc_grads(P, 16, "cuda", zero=True)
+        for t in g.values():
+            t.fill_(0.25 if acc else 9.0)
+        dgr.backward_raw(*args, grads=g, phase="blend")
+        for rows in ((0, 5120), (5120, 5376), (5376, 20992), (20992, P)):
+            dgr.backward_raw(*args, grads=g, accumulate=acc, phase="gaussians", rows=rows)
+        for k in whole:
+            if k == "dL_dconic":
+                continue
+            # same kernels over the same accumulator: only the second blend's reduction order differs from the first
+            err, _ = helpers.grad_errors(g[k] - (0.25 if acc else 0.0), whole[k])
+            assert err <= (5e-4 if k in ("dL_dscale", "dL_drot", "dL_dcov3D") else 2e-5), "%s acc=%d: %.3e" % (k, acc, err)
+    with pytest.raises(dgr.RasterizerError):
+        dgr.backward_raw(*args, phase="gaussians", rows=(100, 300))      # range start must be a multiple of 256

@@ -18,6 +18,16 @@ GRAD_NAMES = ["dL_dmeans2D", "dL_dcolor", "dL_dopacity", "dL_dmeans3D", "dL_dcov
 RENDER_RTOL, RENDER_ATOL = 1e-5, 1e-7   # north_star: rendered channels within 1e-5 relative
 GRAD_TOL = 1e-4                         # north_star: gradients within 1e-4 relative (per-tensor max norm)
 ILL_CONDITIONED = ("dL_dcov3D", "dL_dscale", "dL_drot")   # conic backward amplifies input rounding ~1e3
+# The gates actually enforced are tighter than north_star's 1e-4 wherever the measurements allow: the six well-conditioned
+# tensors measure 1-2e-6 against the reference (its own run-to-run atomic noise), so a 10x regression must fail.  The three
+# ill-conditioned ones are gated against the reference's noise floor and, in test_ill_conditioned_gradients_against_fp64,
+# against an fp64 evaluation of the same formulas.
+WELL_TOL = 1e-5
+
+
+def grad_gate(name):
+    return 5e-4 if name in ILL_CONDITIONED else WELL_TOL
+
 
 
 @pytest.fixture(scope="module")
@@ -61,6 +71,7 @@ CASES = [
     pytest.param(500_000, 800, 800, 9, 3.0, 0.7, id="config3-500k-800x800-F9"),
     pytest.param(500_000, 800, 800, 10, 3.0, 0.7, id="config3-500k-800x800-F10"),
     pytest.param(3_000_000, 1959, 1090, 10, 2.2, 0.0, id="config4-3M-1959x1090-F10"),
+    pytest.param(6_000_000, 1959, 1090, 10, 2.2, 0.0, id="config5-6M-1959x1090-F10"),
 ]
 
 
@@ -77,8 +88,7 @@ def test_forward_and_backward_vs_reference(dgr, ref, P, W, H, F, rad, shell):
         # dL/dcov3D, dL/dscale, dL/drot: the reference's own two runs differ by 1e-4..4e-4 in the max norm at 3 M
         # Gaussians (one noise sample is itself noisy), so their max-norm floor is 5e-4; the relative L2 norm, which is
         # stable, must still meet 1e-4 for every tensor.
-        floor = 5e-4 if k in ILL_CONDITIONED else GRAD_TOL
-        tol = max(floor, 4.0 * noise)
+        tol = max(grad_gate(k), 4.0 * noise)
         assert err <= tol, "%s: max|d|/max|ref| %.3e (l2 %.3e) > %.3e (reference self-noise %.3e)" % (k, err, l2, tol, noise)
         assert l2 <= GRAD_TOL, "%s: relative L2 %.3e" % (k, l2)
 
@@ -112,7 +122,33 @@ def test_random_shapes_vs_reference(dgr, ref, P, W, H, F, rad, shell, scene_seed
             assert float(o[k].abs().max()) == 0.0, k
             continue
         err, l2 = helpers.grad_errors(o[k], r[k])
-        assert err <= (2e-3 if k in ILL_CONDITIONED else 5e-4), "%s: max %.3e l2 %.3e" % (k, err, l2)
+        assert err <= (2e-3 if k in ILL_CONDITIONED else WELL_TOL), "%s: max %.3e l2 %.3e" % (k, err, l2)
+
+
+def test_ill_conditioned_gradients_against_fp64(dgr, ref):
+    """dL/dcov3D, dL/dscale, dL/drot come out of the conic backward (backward.cu:153-281), which amplifies the rounding of its
+    inputs by ~1e3; the reference itself moves by 1e-4..4e-4 between two runs there.  "Inside the reference's noise" is grounded
+    here against a ground truth: the fp64 CPU oracle evaluates the same formulas on the same inputs and the same per-pixel
+    forward state (final_T, n_contrib are bit-identical between the two implementations).  Ours must be as close to it as the
+    reference is (several reference runs give its spread)."""
+    import cpu_rasterizer as cr
+    P, W, H, F = 12_000, 256, 192, 10
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, F, shell=0.7)
+    o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
+    refs = [helpers.run_reference(ref, scene, cam, feats, F, gc, gb) for _ in range(3)]
+    assert torch.equal(o["n_contrib"], refs[0]["n_contrib"]) and torch.equal(helpers.bits(o["final_T"]), helpers.bits(refs[0]["final_T"]))
+    settings = syn.raster_settings_for(syn.camera_to(cam, "cpu"), F, golden_io.Settings)
+    orc = cr.CpuRasterizer(torch.float64)
+    s = syn.scene_to(scene, "cpu")
+    orc.forward(s.means3D, s.shs, None, s.opacities, s.scales, s.rotations, None, feats.cpu(), settings)
+    truth = orc.backward(gc.cpu(), gb.cpu(), final_T=o["final_T"].cpu(), n_contrib=o["n_contrib"].cpu())
+    for k in GRAD_NAMES:
+        mine = helpers.grad_errors(o[k].cpu(), truth[k])[0]
+        theirs = [helpers.grad_errors(r[k].cpu(), truth[k])[0] for r in refs]
+        # as good as the reference: within its own spread of distances to the truth (25 % slack for the three-sample estimate)
+        assert mine <= 1.25 * max(theirs) + 1e-6, "%s: ours %.3e vs reference %s from the fp64 truth" % (k, mine, ["%.3e" % t for t in theirs])
+        if k not in ILL_CONDITIONED:
+            assert mine <= 1e-4, "%s: %.3e from the fp64 truth" % (k, mine)
 
 
 @pytest.mark.parametrize("F", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
@@ -127,7 +163,7 @@ def test_every_feature_count(dgr, ref, F):
     assert float(o["buffer"][F:].abs().max()) == 0.0 if F < 10 else True
     for k in GRAD_NAMES:
         err, _ = helpers.grad_errors(o[k], r[k])
-        assert err <= 5e-4, "%s F=%d err %.3e" % (k, F, err)
+        assert err <= grad_gate(k), "%s F=%d err %.3e" % (k, F, err)
     assert float(o["dL_dfeatures"][:, F:].abs().max()) == 0.0 if F < 10 else True
 
 
@@ -142,7 +178,7 @@ def test_sh_degrees_and_coefficient_counts(dgr, ref, deg, M):
     assert_forward_bit_exact(o, r, P)
     for k in GRAD_NAMES:
         err, _ = helpers.grad_errors(o[k], r[k])
-        assert err <= 5e-4, "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
+        assert err <= grad_gate(k), "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
 
 
 @pytest.mark.parametrize("path", ["depthfirst", "depthfirst-exact", "sort64"])
@@ -340,9 +376,9 @@ def test_precomputed_colors_and_covariances(dgr, ref):
     names = ["dL_dmeans2D", "dL_dcolor", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D"]
     for k, t in zip(names, g_ref[:5]):
         err, _ = helpers.grad_errors(g[k], t)
-        assert err <= 5e-4, "%s err %.3e" % (k, err)
+        assert err <= grad_gate(k), "%s err %.3e" % (k, err)
     err, _ = helpers.grad_errors(g["dL_dfeatures"], g_ref[8])
-    assert err <= 5e-4
+    assert err <= WELL_TOL
     assert float(g["dL_dscale"].abs().max()) == 0.0 and float(g["dL_drot"].abs().max()) == 0.0
 
 
@@ -377,7 +413,7 @@ def test_autograd_surface_matches_reference_binding(dgr, ref):
     for k in g1:
         assert g2[k] is not None and g2[k].shape == g1[k].shape, k
         err, _ = helpers.grad_errors(g2[k], g1[k])
-        assert err <= 5e-4, "%s err %.3e" % (k, err)
+        assert err <= (5e-4 if k in ("scales", "rotations") else WELL_TOL), "%s err %.3e" % (k, err)
 
 
 def test_mark_visible(dgr, ref):
@@ -473,7 +509,7 @@ def test_against_golden_vectors(dgr, path):
                          inp["features"], radii, inp["settings"], state)
     for k in GRAD_NAMES:
         err, _ = helpers.grad_errors(g[k].cpu(), gold[k])
-        assert err <= 5e-4, "%s err %.3e" % (k, err)
+        assert err <= grad_gate(k), "%s err %.3e" % (k, err)
 
 
 def test_against_cpu_oracle(dgr):

@@ -30,11 +30,36 @@ def _fake_view_gradient(v, shape):
     return torch.randn(shape, generator=g)
 
 
-def _worker(rank, world, port, n_views, P, M, out_dir, param_buckets=False):
+def _worker(rank, world, port, n_views, P, M, out_dir, param_buckets=False, deferred=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        def view_stats(v):
+            radii = torch.full((P,), v + 1, dtype=torch.int32)
+            radii[(v + 1) % P] = 0                                  # one culled Gaussian per view
+            observe = torch.zeros(P, dtype=torch.int32)
+            observe[v % P] = 3
+            return radii, observe
+
+        def begin_view(v):                                          # deferred protocol: forward + reverse blend of a view ...
+            radii, observe = view_stats(v)
+            return {"v": v, "radii": radii, "observe": observe}
+
+        def finish_view(h, buckets, accumulate, rows):              # ... and its per-Gaussian stage for a range of Gaussians
+            b, e = rows
+            for name in buckets.names:
+                t = buckets.tensors[name]
+                g = _fake_view_gradient(h["v"] * 31 + len(name), t.shape)[b:e]
+                if accumulate or isinstance(buckets, vp.ParameterBuckets) and name not in ("xyz", "sh"):
+                    t[b:e] += g         # (the packed groups of ParameterBuckets are zeroed by begin_rows and always added to)
+                else:
+                    t[b:e] = g
+            if b == 0:
+                holder["step"].stats.update_backward_eager(_fake_view_gradient(h["v"] * 31 + len("dL_dmeans2D"), (P, 4)), h["radii"])
+
+        holder = {}
+
         def render_view(v, buckets, accumulate):
             for name in buckets.names:
                 t = buckets.tensors[name]
@@ -43,13 +68,16 @@ def _worker(rank, world, port, n_views, P, M, out_dir, param_buckets=False):
                     t += g
                 else:
                     t.copy_(g)          # first view of the step overwrites (kernels write every element)
-            radii = torch.full((P,), v + 1, dtype=torch.int32)
-            radii[(v + 1) % P] = 0                                  # one culled Gaussian per view
-            observe = torch.zeros(P, dtype=torch.int32)
-            observe[v % P] = 3
+            radii, observe = view_stats(v)
             return {"radii": radii, "observe": observe, "means2D_grad": _fake_view_gradient(v * 31 + len("dL_dmeans2D"), (P, 4))}
 
-        step = vp.ViewShardedStep(P, M, "cpu", render_view, buckets_cls=vp.ParameterBuckets if param_buckets else None)
+        cls = vp.ParameterBuckets if param_buckets else None
+        if deferred:
+            step = vp.ViewShardedStep(P, M, "cpu", buckets_cls=cls, begin_view=begin_view, finish_view=finish_view, n_chunks=3)
+            assert len(step.chunks) == 3 and step.chunks[0][0] == 0 and step.chunks[-1][1] == P
+        else:
+            step = vp.ViewShardedStep(P, M, "cpu", render_view, buckets_cls=cls)
+        holder["step"] = step
         assert step.world == world and step.rank == rank
         # poison the buckets: a stale gradient from a previous step must not leak into this one
         for t in step.buckets.tensors.values():
@@ -72,10 +100,11 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("n_views,param_buckets", [(5, False), (1, False), (5, True)])
-def test_two_rank_step_equals_sequential_sum(tmp_path, n_views, param_buckets):
-    world, P, M = 2, 37, 4
-    mp.spawn(_worker, args=(world, _free_port(), n_views, P, M, str(tmp_path), param_buckets), nprocs=world, join=True)
+@pytest.mark.parametrize("n_views,param_buckets,deferred", [(5, False, False), (1, False, False), (5, True, False),
+                                                            (5, False, True), (1, True, True), (5, True, True)])
+def test_two_rank_step_equals_sequential_sum(tmp_path, n_views, param_buckets, deferred):
+    world, P, M = 2, (700 if deferred else 37), 4          # 700 Gaussians: three 256-aligned ranges in the deferred step
+    mp.spawn(_worker, args=(world, _free_port(), n_views, P, M, str(tmp_path), param_buckets, deferred), nprocs=world, join=True)
     res = [torch.load(os.path.join(tmp_path, "rank%d.pt" % r)) for r in range(world)]
     assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(n_views))
     names = vp.ParameterBuckets.names if param_buckets else vp.REDUCED
