@@ -95,7 +95,7 @@ class ClockSampler:
 
 def build_workload(cfg, n_views_total, my_views, device):
     """Replicated scene + this rank's cameras/features, all resident on `device`."""
-    scene = syn.scene_to(syn.make_scene(cfg["P"], shell_fraction=cfg["shell"]), device)
+    scene = syn.scene_to(syn.make_scene(cfg["P"], shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
     cams_cpu = syn.make_cameras(n_views_total, cfg["W"], cfg["H"], radius=cfg["cam_radius"])
     cams = {v: syn.camera_to(cams_cpu[v], device) for v in my_views}
     feats = {v: syn.pack_features(scene, cams[v], cfg["F"]) for v in my_views}
@@ -114,7 +114,7 @@ def run_ours(args, cfg, rank, world, device):
     V_per = args.views_per_rank
     n_views = world * V_per
     my_views = list(vp.shard_views(n_views, world, rank))
-    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"]), device)
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
     cams_cpu = syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])
     cams = {v: syn.camera_to(cams_cpu[v], device) for v in range(n_views)}       # all views: dp_check replays the whole batch
     settings = {v: syn.raster_settings_for(cams[v], F, dgr.GaussianRasterizationSettings) for v in range(n_views)}
@@ -455,7 +455,7 @@ def cpu_baseline(cfg, args, budget_tiles=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     P, W, H, F = cfg["P"], cfg["W"], cfg["H"], cfg["F"]
-    scene = syn.make_scene(P, shell_fraction=cfg["shell"])
+    scene = syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"))
     cam = syn.make_cameras(1, W, H, radius=cfg["cam_radius"])[0]
     feats = syn.pack_features(scene, cam, F)
     gc, gb = syn.make_upstream_grads(W, H, F)

@@ -376,8 +376,10 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
         (a->feature_count > 0 && !a->grad_buffer) || !a->background) {
         set_error("backward: missing saved state / upstream gradient pointer"); return GS2M_ERR_INVALID_ARGUMENT;
     }
-    if (!a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dmeans3D || !a->dL_dcov3D || !a->dL_dscale ||
-        !a->dL_drot || !a->dL_dfeatures || (a->M > 0 && a->shs && !a->dL_dsh)) {
+    // dL_dcolor / dL_dcov3D are the gradients of the PRECOMPUTED colour / covariance inputs: required when those inputs are
+    // used, optional (NULL = not written) when SHs / scale+rotation are
+    if (!a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dmeans3D || !a->dL_dscale || !a->dL_drot || !a->dL_dfeatures ||
+        (a->colors_precomp && !a->dL_dcolor) || (a->cov3D_precomp && !a->dL_dcov3D) || (a->M > 0 && a->shs && !a->dL_dsh)) {
         set_error("backward: missing gradient output pointer"); return GS2M_ERR_INVALID_ARGUMENT;
     }
     if (a->R < 0) { set_error("backward: negative R"); return GS2M_ERR_INVALID_ARGUMENT; }

@@ -38,7 +38,7 @@ constexpr int FWD_CTAS_PER_TILE = BLEND_WARPS / FWD_CTA_WARPS;
 static_assert(BLEND_WARPS % FWD_CTA_WARPS == 0, "CTA must hold a divisor of the tile's 8 warp blocks");
 
 template <int F>
-__global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_forward_kernel(
+__global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_CTA_WARPS) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
     int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,

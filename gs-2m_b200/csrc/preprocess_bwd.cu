@@ -15,6 +15,14 @@
 #include <atomic>
 #include "common.cuh"
 
+// per-Gaussian backward with the SH row kept in registers (see DirectIO) instead of staged through shared memory
+#ifndef GS2M_PB_DIRECT
+#define GS2M_PB_DIRECT 1
+#endif
+#ifndef GS2M_PB_DIRECT_BLOCKS
+#define GS2M_PB_DIRECT_BLOCKS 2      // minimum resident 256-thread blocks per SM the register allocation must allow
+#endif
+
 namespace gs2m {
 namespace {
 
@@ -35,12 +43,8 @@ __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.
 
 // Per-Gaussian backward math, written once; `io` decides where the results go (straight to global memory, or into
 // the block's shared staging rows that are then copied out with coalesced 128-bit stores).
-template <class IO>
-__device__ __forceinline__ void gaussian_backward(const BwdParams& p, const GeomState& g, const int idx, const bool visible, IO& io) {
-    const size_t i = (size_t)idx;
-    const int M = p.M;
-
-    float acc[GS2M_ACC_STRIDE];
+// the Gaussian's packed accumulator row written by the backward blend (zeros for a culled Gaussian)
+__device__ __forceinline__ void load_acc_row(const GeomState& g, size_t i, bool visible, float (&acc)[GS2M_ACC_STRIDE]) {
     if (visible) {
         const float4* a4 = reinterpret_cast<const float4*>(g.grad_acc + i * GS2M_ACC_STRIDE);
 #pragma unroll
@@ -52,6 +56,13 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 #pragma unroll
         for (int k = 0; k < GS2M_ACC_STRIDE; ++k) acc[k] = 0.f;
     }
+}
+
+template <class IO>
+__device__ __forceinline__ void gaussian_backward(const BwdParams& p, const GeomState& g, const int idx, const bool visible,
+                                                  const float (&acc)[GS2M_ACC_STRIDE], IO& io) {
+    const size_t i = (size_t)idx;
+    const int M = p.M;
 
     // a culled Gaussian contributes exactly zero: tensors that are accumulated (+=) need nothing for it, tensors that are
     // overwritten get zeros
@@ -68,7 +79,9 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
         }
         if (!IO::kAccParams) {
             for (int k = 0; k < 3; ++k) io.mean3d(k, 0.f);
-            for (int k = 0; k < 3 * M; ++k) io.sh_out(k, 0.f);
+#pragma unroll
+            for (int k = 0; k < 48; ++k) { if (k < 3 * M) io.sh_out(k, 0.f); }
+            if (IO::kAnyM) { for (int k = 48; k < 3 * M; ++k) io.sh_out(k, 0.f); }
         }
         return;
     }
@@ -257,7 +270,7 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
                 }
             }
         }
-        for (int k = 48; k < 3 * M; ++k) io.sh_out(k, 0.f);
+        if (IO::kAnyM) { for (int k = 48; k < 3 * M; ++k) io.sh_out(k, 0.f); }      // coefficients beyond degree 3 (M > 16)
         // through the normalisation dir = d0/|d0|
         const float s2 = dot(d0, d0);
         const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
@@ -301,7 +314,9 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
         io.rot(make_float4(0.f, 0.f, 0.f, 0.f));
     }
     if (p.shs == nullptr) {
-        for (int k = 0; k < 3 * M; ++k) io.sh_out(k, 0.f);
+#pragma unroll
+        for (int k = 0; k < 48; ++k) { if (k < 3 * M) io.sh_out(k, 0.f); }
+        if (IO::kAnyM) { for (int k = 48; k < 3 * M; ++k) io.sh_out(k, 0.f); }
     }
 }
 
@@ -320,6 +335,7 @@ template <int MODE>
 struct GlobalIO : AccPolicy<MODE> {
     using AccPolicy<MODE>::kAccParams;
     using AccPolicy<MODE>::kAccOther;
+    static constexpr bool kAnyM = true;      // handles rows of more than 48 floats (M > 16)
     const BwdParams& p; size_t i;
     __device__ GlobalIO(const BwdParams& p_, size_t i_) : p(p_), i(i_) {}
     __device__ void mean2d(float4 v) {
@@ -329,10 +345,10 @@ struct GlobalIO : AccPolicy<MODE> {
     }
     __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
     __device__ void opacity(float v) { put<kAccOther>(p.dL_dopacity + i, v); }
-    __device__ void color(int k, float v) { put<kAccOther>(p.dL_dcolor + 3 * i + k, v); }
+    __device__ void color(int k, float v) { if (p.dL_dcolor) put<kAccOther>(p.dL_dcolor + 3 * i + k, v); }
     __device__ void feature(int k, float v) { put<kAccOther>(p.dL_dfeatures + GS2M_NUM_FEATURES * i + k, v); }
     __device__ void mean3d(int k, float v) { put<kAccParams>(p.dL_dmeans3D + 3 * i + k, v); }
-    __device__ void cov(int k, float v) { put<kAccOther>(p.dL_dcov3D + 6 * i + k, v); }
+    __device__ void cov(int k, float v) { if (p.dL_dcov3D) put<kAccOther>(p.dL_dcov3D + 6 * i + k, v); }
     __device__ void scale(int k, float v) { put<kAccOther>(p.dL_dscale + 3 * i + k, v); }
     __device__ void rot(float4 v) {
         float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
@@ -358,6 +374,7 @@ struct StageSmem {
 template <int MODE>
 struct StagedIO : AccPolicy<MODE> {
     using AccPolicy<MODE>::kAccOther;
+    static constexpr bool kAnyM = false;
     const BwdParams& p; size_t i; StageSmem& sm; int t; int sh_row;
     __device__ StagedIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
     __device__ void mean2d(float4 v) {
@@ -379,6 +396,46 @@ struct StagedIO : AccPolicy<MODE> {
     }
     __device__ float sh_in(int k) const { return sm.sh[t * sh_row + k]; }
     __device__ void sh_out(int k, float v) { sm.sh[t * sh_row + k] = v; }
+};
+
+// ---- sink 3: like sink 2 for the short rows, but the SH row never goes through shared memory: the thread holds its own
+// 3*M floats in registers (128-bit loads of its contiguous row, all in flight at once), overwrites them in place with the
+// gradient and writes the row back with 128-bit stores / vector reductions.  Needs 3*M to be a multiple of 4 (M = 4, 8, 12, 16).
+// Shared memory drops from 76 KB to 26 KB per block, so that registers, not shared memory, bound the occupancy and the L1 keeps
+// the sectors two neighbouring 128-bit accesses of a thread share.
+struct SmallSmem {
+    float feat[256 * ST_FEAT];
+    float cov[256 * ST_COV];
+    float mean3d[256 * ST_V3];
+    float scale[256 * ST_V3];
+    float color[256 * ST_V3];
+    unsigned char vis[256];
+};
+template <int MODE>
+struct DirectIO : AccPolicy<MODE> {
+    using AccPolicy<MODE>::kAccOther;
+    static constexpr bool kAnyM = false;
+    const BwdParams& p; size_t i; SmallSmem& sm; int t; float (&shr)[ST_SH];
+    __device__ DirectIO(const BwdParams& p_, size_t i_, SmallSmem& sm_, int t_, float (&shr_)[ST_SH]) : p(p_), i(i_), sm(sm_), t(t_), shr(shr_) {}
+    __device__ void mean2d(float4 v) {
+        float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
+        if (kAccOther) red_add_f4(o, v);
+        else *o = v;
+    }
+    __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
+    __device__ void opacity(float v) { if (kAccOther) atomicAdd(p.dL_dopacity + i, v); else p.dL_dopacity[i] = v; }
+    __device__ void color(int k, float v) { sm.color[t * ST_V3 + k] = v; }
+    __device__ void feature(int k, float v) { sm.feat[t * ST_FEAT + k] = v; }
+    __device__ void mean3d(int k, float v) { sm.mean3d[t * ST_V3 + k] = v; }
+    __device__ void cov(int k, float v) { sm.cov[t * ST_COV + k] = v; }
+    __device__ void scale(int k, float v) { sm.scale[t * ST_V3 + k] = v; }
+    __device__ void rot(float4 v) {
+        float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
+        if (kAccOther) red_add_f4(o, v);
+        else *o = v;
+    }
+    __device__ float sh_in(int k) const { return shr[k]; }
+    __device__ void sh_out(int k, float v) { shr[k] = v; }      // k is a compile-time constant at every call site
 };
 
 // coalesced copy-out of `n` floats of the block's contiguous output region (16-byte aligned start)
@@ -413,7 +470,10 @@ __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdPar
     const int idx = p.row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.row_end) return;
     GlobalIO<MODE> io(p, (size_t)idx);
-    gaussian_backward(p, g, idx, p.radii[idx] > 0, io);
+    const bool visible = p.radii[idx] > 0;
+    float acc[GS2M_ACC_STRIDE];
+    load_acc_row(g, (size_t)idx, visible, acc);
+    gaussian_backward(p, g, idx, visible, acc, io);
 }
 
 template <int MODE>
@@ -428,6 +488,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
     const bool inside = t < rows;
     const bool visible = inside && p.radii[idx] > 0;
     const int sh_row = 3 * p.M;
+    // the thread's own accumulator row is requested first: its latency passes under the cooperative SH staging below
+    float acc[GS2M_ACC_STRIDE];
+    load_acc_row(g, (size_t)(inside ? idx : 0), visible, acc);
     // coalesced load of the SH rows of the block's visible Gaussians
     const int sh_pad = sh_row | 1;
     if (p.shs != nullptr) {
@@ -453,7 +516,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
     sm.vis[t] = visible ? 1 : 0;
     if (inside) {
         StagedIO<MODE> io(p, (size_t)idx, sm, t);
-        gaussian_backward(p, g, idx, visible, io);
+        gaussian_backward(p, g, idx, visible, acc, io);
     }
     __syncthreads();
     if (p.dL_dsh && sh_row > 0) {
@@ -479,10 +542,61 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         }
     }
     block_store<kAccOther, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
-    block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
+    if (p.dL_dcov3D) block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
     block_store<kAccParams, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
     block_store<kAccOther, ST_V3>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
-    block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
+    if (p.dL_dcolor) block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, GS2M_PB_DIRECT_BLOCKS) preprocess_backward_direct_kernel(BwdParams p, GeomState g) {
+    constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
+    __shared__ SmallSmem sm;
+    const int t = threadIdx.x;
+    const size_t row0 = (size_t)p.row_begin + (size_t)blockIdx.x * 256;
+    const int rows = (int)min((size_t)256, (size_t)p.row_end - row0);
+    const int idx = (int)row0 + t;
+    const bool inside = t < rows;
+    const bool visible = inside && p.radii[idx] > 0;
+    const int n4 = (3 * p.M) >> 2;                       // float4s per SH row (3*M is a multiple of 4 here)
+    float acc[GS2M_ACC_STRIDE];
+    load_acc_row(g, (size_t)(inside ? idx : 0), visible, acc);
+    float shr[ST_SH];
+    float4* __restrict__ sh_row_out = p.dL_dsh ? reinterpret_cast<float4*>(p.dL_dsh) + (size_t)idx * n4 : nullptr;
+    if (visible && p.shs != nullptr) {
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(p.shs) + (size_t)idx * n4;
+#pragma unroll
+        for (int j = 0; j < ST_SH / 4; ++j) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n4) v = __ldg(src + j);
+            shr[4 * j] = v.x; shr[4 * j + 1] = v.y; shr[4 * j + 2] = v.z; shr[4 * j + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ST_SH; ++k) shr[k] = 0.f;
+    }
+    sm.vis[t] = visible ? 1 : 0;
+    if (inside) {
+        DirectIO<MODE> io(p, (size_t)idx, sm, t, shr);
+        gaussian_backward(p, g, idx, visible, acc, io);
+        // the thread's SH gradient row: one write per element (zeros for a culled Gaussian when overwriting; nothing when adding)
+        if (sh_row_out != nullptr && (visible || !kAccParams)) {
+#pragma unroll
+            for (int j = 0; j < ST_SH / 4; ++j) {
+                if (j < n4) {
+                    const float4 v = make_float4(shr[4 * j], shr[4 * j + 1], shr[4 * j + 2], shr[4 * j + 3]);
+                    if (kAccParams) red_add_f4(sh_row_out + j, v);
+                    else sh_row_out[j] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    block_store<kAccOther, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
+    if (p.dL_dcov3D) block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
+    block_store<kAccParams, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
+    block_store<kAccOther, ST_V3>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
+    if (p.dL_dcolor) block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
 }
 
 }  // namespace
@@ -492,7 +606,11 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
     const int blocks = (p.row_end - p.row_begin + 255) / 256;
     count_launches(1);
     if (p.accumulate < 0 || p.accumulate > 2) { set_error("accumulate mode %d outside 0..2", p.accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
-    if (p.M <= 16) {
+    if (GS2M_PB_DIRECT && p.M <= 16 && ((3 * p.M) & 3) == 0) {
+        if (p.accumulate == 1) preprocess_backward_direct_kernel<1><<<blocks, 256, 0, s>>>(p, g);
+        else if (p.accumulate == 2) preprocess_backward_direct_kernel<2><<<blocks, 256, 0, s>>>(p, g);
+        else preprocess_backward_direct_kernel<0><<<blocks, 256, 0, s>>>(p, g);
+    } else if (p.M <= 16) {
         static PerDeviceOnce configured;
         int dev;
         if (configured.need(dev)) {

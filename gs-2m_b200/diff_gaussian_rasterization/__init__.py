@@ -206,11 +206,15 @@ _GRAD_SHAPES = (("dL_dmeans2D", 4), ("dL_dconic", 4), ("dL_dopacity", 1), ("dL_d
                 ("dL_dcov3D", 6), ("dL_dscale", 3), ("dL_drot", 4), ("dL_dfeatures", NUM_FEATURES))
 
 
-def alloc_grads(P, M, device, zero=False):
+_OPTIONAL_GRADS = ("dL_dconic", "dL_dcolor", "dL_dcov3D")     # may be None in `grads`: then the kernel does not write them
+
+
+def alloc_grads(P, M, device, zero=False, skip=()):
     """Gradient tensors in the reference's shapes (rasterize_points.cu:150-159). The kernels write every element,
-    so ``torch.empty`` suffices unless the caller wants to accumulate several views (then start from zeros)."""
+    so ``torch.empty`` suffices unless the caller wants to accumulate several views (then start from zeros).  ``skip`` names
+    optional tensors to leave out (``dL_dconic``, and ``dL_dcolor`` / ``dL_dcov3D`` when SHs / scale+rotation are the inputs)."""
     mk = torch.zeros if zero else torch.empty
-    g = {n: mk((P, c), dtype=torch.float32, device=device) for n, c in _GRAD_SHAPES}
+    g = {n: (None if n in skip else mk((P, c), dtype=torch.float32, device=device)) for n, c in _GRAD_SHAPES}
     g["dL_dsh"] = mk((P, M, 3), dtype=torch.float32, device=device)
     return g
 
@@ -258,6 +262,8 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
     for name, c in _GRAD_SHAPES + (("dL_dsh", 3 * M),):
         t = grads.get(name)
         if name == "dL_dsh" and M == 0:
+            continue
+        if t is None and (name == "dL_dconic" or (name == "dL_dcolor" and col_t is None) or (name == "dL_dcov3D" and cov_t is None)):
             continue
         if t is None or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * c:
             raise RuntimeError("grads[%r] must be a contiguous float32 tensor with %d x %d elements on %s" % (name, P, c, dev))
@@ -379,8 +385,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         (means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp, features, radii,
          geom, binning, img) = ctx.saved_tensors
         state = ctx.raster_state      # (the arenas travel through save_for_backward so that autograd tracks their lifetime)
+        # gradients nobody receives are not computed: dL_dconic always, dL_dcolor / dL_dcov3D when those inputs are absent
+        skip = ("dL_dconic",) + (("dL_dcolor",) if _absent(colors_precomp) else ()) + (("dL_dcov3D",) if _absent(cov3Ds_precomp) else ())
+        P_, M_ = int(means3D.shape[0]), (0 if _absent(shs) else int(shs.shape[1]))
         g = backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3Ds_precomp,
-                         features, radii, ctx.raster_settings, state)
+                         features, radii, ctx.raster_settings, state, grads=alloc_grads(P_, M_, means3D.device, skip=skip))
         # slots: means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, features, settings
         return (g["dL_dmeans3D"], g["dL_dmeans2D"],
                 None if _absent(shs) else g["dL_dsh"],

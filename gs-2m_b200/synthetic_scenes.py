@@ -20,6 +20,9 @@ CONFIGS = {
     "shiny-500k": dict(P=500_000, W=800, H=800, F=9, views=8, cam_radius=3.0, shell=0.7),
     "tnt-3m": dict(P=3_000_000, W=1959, H=1090, F=10, views=8, cam_radius=2.2, shell=0.0),
     "dp-6m": dict(P=6_000_000, W=1959, H=1090, F=10, views=64, cam_radius=2.2, shell=0.0),
+    # load-imbalance probe (not a BASELINE config): 40 % of the Gaussians in a tight blob at the origin, so that a few dozen
+    # tiles carry lists more than ten times the mean length
+    "clustered-1m": dict(P=1_000_000, W=1959, H=1090, F=10, views=8, cam_radius=2.2, shell=0.0, cluster=(0.4, 0.02)),
 }
 
 
@@ -44,7 +47,9 @@ class Camera(NamedTuple):
     camera_center: torch.Tensor         # (3,)
 
 
-def make_scene(P, seed=SCENE_SEED, shell_fraction=0.0, extent=1.0):
+def make_scene(P, seed=SCENE_SEED, shell_fraction=0.0, extent=1.0, cluster=None):
+    """``cluster = (fraction, sigma)``: that fraction of the Gaussians (taken from the end of the arrays) is moved into an
+    isotropic normal blob of that standard deviation around the origin (a dense object in a sparse scene)."""
     g = torch.Generator().manual_seed(seed)
     means = (torch.rand(P, 3, generator=g) * 2.0 - 1.0) * extent
     if shell_fraction > 0:
@@ -67,6 +72,10 @@ def make_scene(P, seed=SCENE_SEED, shell_fraction=0.0, extent=1.0):
     albedo = torch.sigmoid(torch.randn(P, 3, generator=g))
     roughness = torch.sigmoid(torch.randn(P, 1, generator=g))
     metallic = torch.sigmoid(torch.randn(P, 1, generator=g))
+    if cluster is not None:
+        n_cl = int(P * cluster[0])
+        if n_cl > 0:
+            means[P - n_cl:] = cluster[1] * torch.randn(n_cl, 3, generator=g)
     return Scene(means.float(), scales.float(), rotations.float(), opacities.float(), shs.float(), albedo.float(),
                  roughness.float(), metallic.float())
 

@@ -112,15 +112,15 @@ class GradientBuckets:
         self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
         self.tensors: Dict[str, torch.Tensor] = {
             n: self.flat[offsets[n]:offsets[n] + numel(shapes[n])].view(shapes[n]) for n in self.names}
-        # per-view scratch of the backward (never reduced), but the C-ABI wants a pointer for each
+        # gradients nobody consumes here (those of the precomputed colour / covariance inputs, the conic scratch) are not
+        # computed at all: the C-ABI takes NULL for them
         for n in shapes:
             if n not in self.tensors:
-                self.tensors[n] = torch.zeros(shapes[n], dtype=torch.float32, device=device)
+                self.tensors[n] = None
         self.views_accumulated = 0
 
     def zero_(self):
-        for t in self.tensors.values():
-            t.zero_()
+        self.flat.zero_()
         self.views_accumulated = 0
 
     def nbytes_reduced(self) -> int:
@@ -179,8 +179,9 @@ class ParameterBuckets:
         self._packed_from = offsets["scaling"]                   # everything behind xyz and sh comes from chain_view
         # per-view scratch: the rasterizer-side gradients that are consumed by chain_view (or unused by GS-2M)
         z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)  # noqa: E731
+        # (dL_dconic / dL_dcolor / dL_dcov3D have no consumer in GS-2M's chain: NULL, the kernel skips them)
         self.raster = {"dL_dmeans3D": self.tensors["xyz"], "dL_dsh": self.tensors["sh"], "dL_dmeans2D": z(P, 4),
-                       "dL_dconic": z(P, 4), "dL_dopacity": z(P, 1), "dL_dcolor": z(P, 3), "dL_dcov3D": z(P, 6),
+                       "dL_dconic": None, "dL_dopacity": z(P, 1), "dL_dcolor": None, "dL_dcov3D": None,
                        "dL_dscale": z(P, 3), "dL_drot": z(P, 4), "dL_dfeatures": z(P, 10)}
         self.views_accumulated = 0
 

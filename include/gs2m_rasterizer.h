@@ -138,9 +138,9 @@ typedef struct gs2m_backward_args {
     float* dL_dmeans2D;         /* [P,4]  (.xy signed, .zw sum of |.|)  rasterize_points.cu:151 */
     float* dL_dconic;           /* [P,4]  scratch-like output (x,y,-,w) rasterize_points.cu:154 */
     float* dL_dopacity;         /* [P,1] */
-    float* dL_dcolor;           /* [P,3] */
+    float* dL_dcolor;           /* [P,3]  gradient of colors_precomp; may be NULL (not written) when shs are used */
     float* dL_dmeans3D;         /* [P,3] */
-    float* dL_dcov3D;           /* [P,6] */
+    float* dL_dcov3D;           /* [P,6]  gradient of cov3D_precomp; may be NULL (not written) when scales+rotations are used */
     float* dL_dsh;              /* [P,M,3] or NULL when M == 0 */
     float* dL_dscale;           /* [P,3] */
     float* dL_drot;             /* [P,4] */

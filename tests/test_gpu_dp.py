@@ -71,8 +71,7 @@ def _worker(rank, world, port, out_dir, n_streams, deferred=False):
                                                        finish_view=holder["deferred"][1], n_chunks=3)
         else:
             step = holder["step"] = vp.ViewShardedStep(P, 16, device, render, n_streams=n_streams)
-        for t in step.buckets.tensors.values():
-            t.fill_(7.0)                                    # stale content must not leak into the step
+        step.buckets.flat.fill_(7.0)                                    # stale content must not leak into the step
         grads = step.run(N_VIEWS)
         torch.cuda.synchronize(device)
         torch.save({"grads": {k: grads[k].cpu() for k in step.buckets.names}, "stats": step.stats.flat.cpu()},

@@ -80,8 +80,7 @@ def _worker(rank, world, port, n_views, P, M, out_dir, param_buckets=False, defe
         holder["step"] = step
         assert step.world == world and step.rank == rank
         # poison the buckets: a stale gradient from a previous step must not leak into this one
-        for t in step.buckets.tensors.values():
-            t.fill_(123.0)
+        step.buckets.flat.fill_(123.0)
         grads = step.run(n_views)
         torch.save({"grads": {k: grads[k].clone() for k in step.buckets.names}, "radii": step.stats.max_radii2D.clone(),
                     "observe": step.stats.observe_cnt.clone(), "accum": step.stats.xyz_gradient_accum.clone(),

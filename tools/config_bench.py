@@ -34,7 +34,7 @@ def make_leaves(scene):
 
 def time_impl(mod, cfg, F, n_views, iters, warmup, device):
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
-    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"]), device)
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
     cams = [syn.camera_to(c, device) for c in syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])]
     feats = [syn.pack_features(scene, c, F).requires_grad_(True) for c in cams]
     gc, gb = [t.to(device) for t in syn.make_upstream_grads(W, H, F)]
@@ -84,9 +84,49 @@ def time_impl(mod, cfg, F, n_views, iters, warmup, device):
             "visible": int((info["visible"] > 0).sum())}
 
 
+def time_graphed(dgr, cfg, F, n_views, iters, device):
+    """The same views with forward (no_wait: nothing touches the host) + backward captured ONCE into a CUDA graph per view and
+    replayed: what the kernels cost without Python, ctypes and per-kernel launch overhead (fixed shapes; the camera matrices
+    live in static buffers a caller would refresh with three tiny copies)."""
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
+    cams = [syn.camera_to(c, device) for c in syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])]
+    feats = [syn.pack_features(scene, c, F) for c in cams]
+    gc, gb = [t.to(device) for t in syn.make_upstream_grads(W, H, F)]
+    settings = [syn.raster_settings_for(c, F, dgr.GaussianRasterizationSettings) for c in cams]
+    graphs = []
+    side = torch.cuda.Stream()
+    for v in range(n_views):
+        args = (scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None, feats[v], settings[v])
+        cap = int(1.25 * dgr.forward_raw(*args, capacity=0)[4].num_rendered) + 65536
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            out = dgr.forward_raw(*args, capacity=cap, no_wait=True)
+            dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v], out[1],
+                             settings[v], out[4])
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = dgr.forward_raw(*args, capacity=cap, no_wait=True)
+            grads = dgr.backward_raw(gc, gb, scene.means3D, scene.shs, None, scene.scales, scene.rotations, None, feats[v],
+                                     out[1], settings[v], out[4])
+        graphs.append((g, out, grads))
+    for g, _, _ in graphs:
+        g.replay()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        for g, _, _ in graphs:
+            g.replay()
+    e1.record()
+    torch.cuda.synchronize(device)
+    return {"ms_per_view": e0.elapsed_time(e1) / (iters * n_views)}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="plumbing-100k,dtu-300k,shiny-500k,shiny-500k:10,tnt-3m")
+    ap.add_argument("--configs", default="plumbing-100k,dtu-300k,shiny-500k,shiny-500k:10,tnt-3m,clustered-1m")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views-per-iter", type=int, default=2)
@@ -106,6 +146,9 @@ def main():
         iters = args.iters if cfg["P"] < 2_000_000 else max(3, args.iters // 3)
         row = {"config": cname, "P": cfg["P"], "W": cfg["W"], "H": cfg["H"], "F": F, "views_per_iter": args.views_per_iter}
         row["ours"] = time_impl(dgr, cfg, F, args.views_per_iter, iters, args.warmup, device)
+        torch.cuda.empty_cache()
+        row["ours_graph"] = time_graphed(dgr, cfg, F, args.views_per_iter, iters, device)
+        torch.cuda.empty_cache()
         if ref is not None:
             row["reference"] = time_impl(ref, cfg, F, args.views_per_iter, iters, args.warmup, device)
             row["speedup"] = row["reference"]["ms_per_view"] / row["ours"]["ms_per_view"]
@@ -117,13 +160,13 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(rows, f, indent=1)
-    print("| config | P | image | F | ours ms/view (fwd / bwd) | reference ms/view (fwd / bwd) | speed-up (device / wall) |")
-    print("|---|---|---|---|---|---|---|")
+    print("| config | P | image | F | ours ms/view (fwd / bwd) | ours, CUDA-graph replay | reference ms/view (fwd / bwd) | speed-up (device / wall) |")
+    print("|---|---|---|---|---|---|---|---|")
     for r in rows:
         o = r["ours"]
         rr = r.get("reference")
-        print("| %s | %d | %dx%d | %d | %.3f (%.3f / %.3f) | %s | %s |" % (
-            r["config"], r["P"], r["W"], r["H"], r["F"], o["ms_per_view"], o["fwd_ms"], o["bwd_ms"],
+        print("| %s | %d | %dx%d | %d | %.3f (%.3f / %.3f) | %.3f | %s | %s |" % (
+            r["config"], r["P"], r["W"], r["H"], r["F"], o["ms_per_view"], o["fwd_ms"], o["bwd_ms"], r["ours_graph"]["ms_per_view"],
             "%.3f (%.3f / %.3f)" % (rr["ms_per_view"], rr["fwd_ms"], rr["bwd_ms"]) if rr else "-",
             "%.2fx / %.2fx" % (r["speedup"], r["speedup_wall"]) if rr else "-"))
 

@@ -16,7 +16,8 @@ from diff_gaussian_rasterization import _native  # noqa: E402
 cfg_name = sys.argv[1] if len(sys.argv) > 1 else "tnt-3m"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 cfg = syn.CONFIGS[cfg_name]
-scene, cam, feats, gc, gb = helpers.make_view(cfg["P"], cfg["W"], cfg["H"], cfg["F"], shell=cfg["shell"], cam_radius=cfg["cam_radius"])
+scene, cam, feats, gc, gb = helpers.make_view(cfg["P"], cfg["W"], cfg["H"], cfg["F"], shell=cfg["shell"], cam_radius=cfg["cam_radius"],
+                                              cluster=cfg.get("cluster"))
 lib = _native.load()
 for _ in range(3):
     helpers.run_ours(dgr, scene, cam, feats, cfg["F"], gc, gb)
@@ -32,6 +33,10 @@ for k, (ms, n) in st.items():
     print("%-16s %8.4f ms" % (k, ms / max(n, 1)))
     tot += ms / max(n, 1)
 print("%-16s %8.4f ms" % ("sum", tot))
+o = helpers.run_ours(dgr, scene, cam, feats, cfg["F"])
+ln = (o["ranges"][:, 1] - o["ranges"][:, 0]).float()
+print("R = %d, visible = %d, tile lists: mean %.0f, max %d (%.1fx mean); mean n_contrib %.1f" % (
+    o["R"], int((o["radii"] > 0).sum()), float(ln.mean()), int(ln.max()), float(ln.max() / ln.mean().clamp_min(1)), float(o["n_contrib"].float().mean())))
 
 # ---- host-side view: wall time per fwd+bwd (one sync at the end) and host time spent inside each call ----
 import time
