@@ -218,45 +218,51 @@ def run_ours(args, cfg, rank, world, device):
     h_loss = torch.zeros(len(my_views), dtype=torch.float32).pin_memory()
     bg = torch.zeros(3, device=device)
     copy_stream = torch.cuda.Stream(device=device)
-    # every view of the step keeps its camera slot until its per-Gaussian stage has run (deferred): one slot per view
-    slots = [dict(gt=torch.empty((3, H, W), device=device), wvt=torch.empty((4, 4), device=device),
-                  full=torch.empty((4, 4), device=device), cpos=torch.empty(3, device=device),
-                  ready=torch.cuda.Event()) for _ in range(len(my_views))]
+    # camera matrices (tiny) are read again by the view's deferred per-Gaussian stage: one slot per view, double-buffered over
+    # steps so that the next step's copies never wait for this step's tail; the ground-truth images (25.6 MB each) are only
+    # needed until the view's loss gradient is formed: a ring of one slot per local view
+    n_ahead = min(4, len(my_views))       # a view's copies are queued this many views ahead of its forward
+    cam_slots = [[dict(wvt=torch.empty((4, 4), device=device), full=torch.empty((4, 4), device=device),
+                       cpos=torch.empty(3, device=device)) for _ in my_views] for _ in range(2)]
+    gt_slots = [dict(gt=torch.empty((3, H, W), device=device), ready=torch.cuda.Event(), free=torch.cuda.Event())
+                for _ in range(len(my_views))]
     h2d = sum(t.numel() * 4 for t in h_cam[my_views[0]]) + h_gt.numel() * 4
     d2h = 4
-    n_ahead = max(args.streams, 1)        # views in flight (one per stream); each view prefetches the one n_ahead later
-    step_done = torch.cuda.Event()
+    seq = {"k": 0}          # views begun so far, over all steps: view k of the run is view k % n of step k // n
 
-    def prefetch(pos):
-        sl, v = slots[pos], my_views[pos]
+    def prefetch(k, pos, parity):
+        sl, cs, v = gt_slots[k % len(gt_slots)], cam_slots[parity][pos], my_views[pos]
         with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl["free"])
             sl["gt"].copy_(h_gt, non_blocking=True)
-            sl["wvt"].copy_(h_cam[v][0], non_blocking=True)
-            sl["full"].copy_(h_cam[v][1], non_blocking=True)
-            sl["cpos"].copy_(h_cam[v][2], non_blocking=True)
+            cs["wvt"].copy_(h_cam[v][0], non_blocking=True)
+            cs["full"].copy_(h_cam[v][1], non_blocking=True)
+            cs["cpos"].copy_(h_cam[v][2], non_blocking=True)
             sl["ready"].record(copy_stream)
 
     def begin_view_e2e(v):
-        pos = my_views.index(v)
-        if pos == 0:
-            copy_stream.wait_event(step_done)      # the previous step's per-Gaussian stage has read every slot
-            for j in range(min(n_ahead, len(my_views))):
-                prefetch(j)
-        if pos + n_ahead < len(my_views):
-            prefetch(pos + n_ahead)
-        sl = slots[pos]
+        pos, k, n = my_views.index(v), seq["k"], len(my_views)
+        parity = (k // n) & 1
+        if k == 0:
+            for j in range(n_ahead):
+                prefetch(j, j % n, (j // n) & 1)
+        kk = k + n_ahead                              # global index of the view prefetched now (may belong to the next step)
+        prefetch(kk, kk % n, (kk // n) & 1)
+        sl, cs = gt_slots[k % len(gt_slots)], cam_slots[parity][pos]
         torch.cuda.current_stream(device).wait_event(sl["ready"])
-        st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, sl["wvt"],
-                                               sl["full"], 3, sl["cpos"], False, F)
+        st = dgr.GaussianRasterizationSettings(H, W, cams_cpu[v].tanfovx, cams_cpu[v].tanfovy, bg, 1.0, cs["wvt"],
+                                               cs["full"], 3, cs["cpos"], False, F)
 
         def grad_color(color):
             diff = color - sl["gt"]
             h_loss[pos].copy_((diff * diff).mean(), non_blocking=True)
-            return diff * (2.0 / diff.numel())
+            g_c = diff * (2.0 / diff.numel())
+            sl["free"].record(torch.cuda.current_stream(device))
+            return g_c
+        seq["k"] = k + 1
         return begin_view(v, grad_color=grad_color, st=st)
 
     step_e2e = make_step(begin_view_e2e, buckets=step.buckets)
-    step_done.record(torch.cuda.current_stream(device))
 
     def run_e2e(steps):
         holder["step"] = step_e2e
@@ -266,7 +272,6 @@ def run_ours(args, cfg, rank, world, device):
         e0.record()
         for _ in range(steps):
             step_e2e.run(n_views)
-            step_done.record(torch.cuda.current_stream(device))
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -359,6 +364,8 @@ def run_ours(args, cfg, rank, world, device):
         fl = {v: feats[v].clone().requires_grad_(True) for v in my_views[:2]}
 
         def iteration():
+            for t in list(leaves.values()) + list(fl.values()) + [m2d]:
+                t.grad = None                                   # optimizer.zero_grad(set_to_none=True), train.py:259
             for v in my_views[:2]:
                 color, radii, observe, buffer = dgr.GaussianRasterizer(settings[v])(
                     means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"], colors_precomp=None,
@@ -380,7 +387,8 @@ def run_ours(args, cfg, rank, world, device):
         dropin = {"value": round(n_v / (d_ms * 1e-3), 3), "unit": UNIT, "ms_per_view": round(d_ms / n_v, 4),
                   "wall_ms_per_view": round(d_wall / n_v, 4),
                   "what": "GaussianRasterizer(settings)(...) + torch.autograd.backward on torch's current stream, 2 views per "
-                          "iteration, .grad accumulation by autograd (rasterizer only, like the reference arm)"}
+                          "iteration, .grad set to None per iteration and accumulated by autograd (rasterizer only, like the "
+                          "reference arm)"}
 
     if rank != 0:
         return None

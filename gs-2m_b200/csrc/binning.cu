@@ -178,16 +178,6 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const KeyT* __
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-// exclusive scan of each pass's 256 bins (one CTA per pass)
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sw[8];
-    uint32_t* h = hist + blockIdx.x * RS_RADIX;
-    const uint32_t v = h[threadIdx.x];
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan(v, sw, total);
-    h[threadIdx.x] = ex;
-}
-
 // One digit pass. Keys are held warp-striped: warp w owns keys [w*32*ITEMS, (w+1)*32*ITEMS) of the tile and lane l
 // holds items l, l+32, ...; stable order inside the tile is therefore (warp, item, lane).
 template <typename KeyT>
@@ -196,7 +186,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __r
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ vals_out, int n_cap,
                                                                  const uint32_t* __restrict__ n_ptr, int shift, int bits,
-                                                                 const uint32_t* __restrict__ digit_base /*[256]*/,
+                                                                 const uint32_t* __restrict__ digit_hist /*[256] counts of this digit*/,
                                                                  volatile uint32_t* __restrict__ status /*[tiles][256]*/,
                                                                  uint32_t* __restrict__ ticket) {
     // The grid covers the capacity; CTAs beyond the real count leave before taking a ticket, so tickets 0..ceil(n/TILE)-1 are
@@ -277,8 +267,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __r
         }
         uint32_t tile_total;
         const uint32_t tile_off = block_exclusive_scan(count, s_scan, tile_total);
+        // first output slot of digit d = exclusive scan of the digit's global histogram (every CTA redoes this 256-element scan:
+        // cheaper than a separate one-block kernel between the histogram and the first pass)
+        const uint32_t digit_base = block_exclusive_scan(digit_hist[d], s_scan, tile_total);
         s_tile_off[d] = tile_off;
-        s_base[d] = digit_base[d] + exclusive - tile_off;
+        s_base[d] = digit_base + exclusive - tile_off;
     }
     __syncthreads();
 
@@ -358,9 +351,8 @@ static int sort_pairs_pingpong_t(KeyT* keys_in, KeyT* keys_out, uint32_t* vals_i
     GS2M_CUDA(cudaMemsetAsync(hist, 0, (size_t)((char*)(status + (size_t)passes * tiles * RS_RADIX) - (char*)hist), s));
     int hist_blocks = (n + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-    count_launches(2 + passes);
+    count_launches(1 + passes);
     rs_histogram_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, s>>>(keys_in, n, n_ptr, passes, end_bit, hist);
-    rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
     KeyT* kbuf[2] = {keys_in, keys_out};
     uint32_t* vbuf[2] = {vals_in, vals_out};
     int src = 0;

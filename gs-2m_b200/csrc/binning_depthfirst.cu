@@ -140,8 +140,7 @@ __global__ void __launch_bounds__(CS_THREADS) compact_apply_kernel(const uint32_
     }
 }
 
-// inclusive scan of tiles_touched[order[i]]: same three-kernel scheme on one counter.  One Gaussian per thread (EMIT_ITEMS):
-// the emission loop behind the scan is serial per thread, so more items per thread only lengthens the critical path.
+// inclusive scan of tiles_touched[order[i]]: same three-kernel scheme on one counter, one Gaussian per thread
 constexpr int EMIT_ITEMS = 1;
 constexpr int EMIT_TILE = CS_THREADS * EMIT_ITEMS;
 
@@ -162,7 +161,12 @@ __global__ void __launch_bounds__(CS_THREADS) ordered_tile_sums_kernel(const uin
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// scan apply fused with the emission: thread handles EMIT_ITEMS consecutive depth ranks and writes their instances
+// scan apply fused with the emission.  A thread owns one depth rank (its Gaussian's tile rectangle and instance count); the
+// instances themselves are written WARP-COOPERATIVELY: the warp's 32 Gaussians occupy one contiguous slice of the output, lane l
+// writes slots l, l+32, ... of that slice and finds the Gaussian a slot belongs to by a 5-step search over the lanes' exclusive
+// offsets.  Every store instruction therefore covers 32 consecutive (tile id, index) pairs, and a screen-filling splat is spread
+// over the whole warp instead of serialising one thread (the per-thread loops of duplicateWithKeys, rasterizer_impl.cu:63-103).
+// The order inside the slice is unchanged: by Gaussian (depth rank), then row-major over its rectangle.
 __global__ void __launch_bounds__(CS_THREADS) emit_in_depth_order_kernel(const uint32_t* __restrict__ tiles_touched,
                                                                          const uint32_t* __restrict__ order, int n_cap,
                                                                          const uint32_t* __restrict__ n_ptr,
@@ -174,29 +178,44 @@ __global__ void __launch_bounds__(CS_THREADS) emit_in_depth_order_kernel(const u
     __shared__ uint2 sw[8];
     const int n = n_ptr ? (int)min(*n_ptr, (uint32_t)n_cap) : n_cap;
     if ((int)(blockIdx.x * EMIT_TILE) >= n) return;
-    const int base = blockIdx.x * EMIT_TILE + threadIdx.x * EMIT_ITEMS;
-    uint32_t t[EMIT_ITEMS], id[EMIT_ITEMS];
-    uint2 s = make_uint2(0, 0);
-#pragma unroll
-    for (int i = 0; i < EMIT_ITEMS; ++i) {
-        id[i] = (base + i < n) ? order[base + i] : 0u;
-        t[i] = (base + i < n) ? tiles_touched[id[i]] : 0u;
-        s.x += t[i];
+    const int rank = blockIdx.x * EMIT_TILE + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t id = (rank < n) ? order[rank] : 0u;
+    const uint32_t count = (rank < n) ? tiles_touched[id] : 0u;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (count != 0u) {
+        const float4 rec = xy_conic_ab[id];
+        tile_rect(rec.x, rec.y, radii[id], tiles_x, tiles_y, x0, y0, x1, y1);
     }
     uint2 total;
-    uint32_t off = block_exclusive_scan2(s, sw, total).x + tile_offsets[blockIdx.x].x;
-#pragma unroll 1
-    for (int i = 0; i < EMIT_ITEMS; ++i) {
-        if (t[i] == 0u) continue;
-        const float4 rec = xy_conic_ab[id[i]];
-        int x0, y0, x1, y1;
-        tile_rect(rec.x, rec.y, radii[id[i]], tiles_x, tiles_y, x0, y0, x1, y1);
-        for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) {
-                tile_keys[off] = (uint32_t)(y * tiles_x + x);
-                vals[off] = id[i];
-                ++off;
-            }
+    const uint32_t off = block_exclusive_scan2(make_uint2(count, 0u), sw, total).x + tile_offsets[blockIdx.x].x;
+    // the warp's slice: [base, base + warp_total); `rel` = this lane's exclusive offset inside it
+    const uint32_t base = __shfl_sync(0xffffffffu, off, 0);
+    const uint32_t rel = off - base;
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, rel + count, 31);
+    const int rect_w = x1 - x0;
+    for (uint32_t j0 = 0; j0 < warp_total; j0 += 32) {       // warp-uniform trip count: every lane takes part in the shuffles
+        const uint32_t j = j0 + (uint32_t)lane;
+        const bool active = j < warp_total;
+        // owner = the largest lane whose exclusive offset is <= j (lanes with no instances share their successor's offset and
+        // can only be picked when they are followed by no instance at all, which j < warp_total excludes)
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = owner + step;
+            const uint32_t r = __shfl_sync(0xffffffffu, rel, cand & 31);
+            if (cand < 32 && r <= j) owner = cand;
+        }
+        const uint32_t o_rel = __shfl_sync(0xffffffffu, rel, owner);
+        const int o_x0 = __shfl_sync(0xffffffffu, x0, owner), o_y0 = __shfl_sync(0xffffffffu, y0, owner);
+        const int o_w = __shfl_sync(0xffffffffu, rect_w, owner);
+        const uint32_t o_id = __shfl_sync(0xffffffffu, id, owner);
+        if (active) {
+            const uint32_t m = j - o_rel;
+            const uint32_t row = m / (uint32_t)o_w, col = m - row * (uint32_t)o_w;
+            tile_keys[base + j] = (uint32_t)((o_y0 + (int)row) * tiles_x + o_x0 + (int)col);
+            vals[base + j] = o_id;
+        }
     }
 }
 

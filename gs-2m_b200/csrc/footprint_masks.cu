@@ -12,6 +12,8 @@ namespace {
 // (identifyTileRanges, rasterizer_impl.cu:108-129): the sorted key gives the tile, the sorted value the Gaussian.
 // KeyT = uint64_t: the reference's (tile << 32 | depth) keys.  KeyT = uint32_t: bare tile ids of the depth-first binning
 // path; the 64-bit key of every instance is then re-materialised into keys64_out (the parity surface of the sort).
+constexpr int RM_ITEMS = 2;      // instances per thread: the record gathers of both are in flight together (the kernel is
+                                 // bound by the latency of those gathers, ncu: long_scoreboard 54 % with one instance per thread)
 template <typename KeyT>
 __global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R_cap, const uint32_t* __restrict__ n_ptr, int tiles_x,
                                                                const KeyT* __restrict__ keys,
@@ -20,25 +22,49 @@ __global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R_cap, const 
                                                                const float* __restrict__ depths, uint64_t* __restrict__ keys64_out,
                                                                uint2* __restrict__ ranges, uint8_t* __restrict__ masks) {
     const int R = n_ptr ? (int)min(*n_ptr, (uint32_t)R_cap) : R_cap;   // grid covers the capacity, the count lives on the device
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
     constexpr int SHIFT = sizeof(KeyT) == 8 ? 32 : 0;
-    const uint32_t tile = (uint32_t)(keys[i] >> SHIFT);
-    if (i == 0) {
-        ranges[tile].x = 0;
-    } else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> SHIFT);
-        if (prev != tile) {
-            ranges[prev].y = (uint32_t)i;
-            ranges[tile].x = (uint32_t)i;
+    const int i0 = blockIdx.x * (256 * RM_ITEMS) + threadIdx.x;
+    if (blockIdx.x * (256 * RM_ITEMS) >= R) return;
+    uint32_t tile[RM_ITEMS], prev[RM_ITEMS], gid[RM_ITEMS];
+    float4 ra[RM_ITEMS], rb[RM_ITEMS];
+    float dep[RM_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RM_ITEMS; ++k) {
+        const int i = i0 + k * 256;
+        tile[k] = prev[k] = gid[k] = 0u;
+        if (i < R) {
+            tile[k] = (uint32_t)(keys[i] >> SHIFT);
+            prev[k] = (i > 0) ? (uint32_t)(keys[i - 1] >> SHIFT) : 0u;
+            gid[k] = point_list[i];
         }
     }
-    if (i == R - 1) ranges[tile].y = (uint32_t)R;
-    const uint32_t gid = point_list[i];
-    if (sizeof(KeyT) == 4) keys64_out[i] = ((uint64_t)tile << 32) | (uint64_t)__float_as_uint(__ldg(depths + gid));
-    const CullRecord cr = make_cull_record(__ldg(rec_a + gid), __ldg(rec_b + gid));
-    const int ty = (int)(tile / (uint32_t)tiles_x), tx = (int)(tile - (uint32_t)ty * (uint32_t)tiles_x);
-    masks[i] = (uint8_t)warp_block_mask(cr, tx * GS2M_TILE_X, ty * GS2M_TILE_Y);
+#pragma unroll
+    for (int k = 0; k < RM_ITEMS; ++k) {
+        const int i = i0 + k * 256;
+        ra[k] = rb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dep[k] = 0.f;
+        if (i < R) {
+            ra[k] = __ldg(rec_a + gid[k]);
+            rb[k] = __ldg(rec_b + gid[k]);
+            if (sizeof(KeyT) == 4) dep[k] = __ldg(depths + gid[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RM_ITEMS; ++k) {
+        const int i = i0 + k * 256;
+        if (i >= R) continue;
+        if (i == 0) {
+            ranges[tile[k]].x = 0;
+        } else if (prev[k] != tile[k]) {
+            ranges[prev[k]].y = (uint32_t)i;
+            ranges[tile[k]].x = (uint32_t)i;
+        }
+        if (i == R - 1) ranges[tile[k]].y = (uint32_t)R;
+        if (sizeof(KeyT) == 4) keys64_out[i] = ((uint64_t)tile[k] << 32) | (uint64_t)__float_as_uint(dep[k]);
+        const CullRecord cr = make_cull_record(ra[k], rb[k]);
+        const int ty = (int)(tile[k] / (uint32_t)tiles_x), tx = (int)(tile[k] - (uint32_t)ty * (uint32_t)tiles_x);
+        masks[i] = (uint8_t)warp_block_mask(cr, tx * GS2M_TILE_X, ty * GS2M_TILE_Y);
+    }
 }
 
 }  // namespace
@@ -48,7 +74,7 @@ int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* key
     GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
     if (R > 0) {
         count_launches(1);
-        ranges_and_masks_kernel<uint64_t><<<(R + 255) / 256, 256, 0, s>>>(R, nullptr, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
+        ranges_and_masks_kernel<uint64_t><<<(R + 256 * RM_ITEMS - 1) / (256 * RM_ITEMS), 256, 0, s>>>(R, nullptr, tiles_x, keys_sorted, point_list, g.xy_conic_ab,
                                                                           g.conic_c_opac, nullptr, nullptr, ranges, masks);
         GS2M_CUDA(cudaGetLastError());
     }
@@ -62,7 +88,7 @@ int launch_ranges_masks_keys(int R_cap, const uint32_t* n_ptr, int tiles_x, int 
     GS2M_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles_x * tiles_y * sizeof(uint2), s));
     if (R_cap > 0) {
         count_launches(1);
-        ranges_and_masks_kernel<uint32_t><<<(R_cap + 255) / 256, 256, 0, s>>>(R_cap, n_ptr, tiles_x, tile_keys_sorted, point_list,
+        ranges_and_masks_kernel<uint32_t><<<(R_cap + 256 * RM_ITEMS - 1) / (256 * RM_ITEMS), 256, 0, s>>>(R_cap, n_ptr, tiles_x, tile_keys_sorted, point_list,
                                                                               g.xy_conic_ab, g.conic_c_opac, g.depths, keys64_out,
                                                                               ranges, masks);
         GS2M_CUDA(cudaGetLastError());

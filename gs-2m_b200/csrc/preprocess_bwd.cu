@@ -15,16 +15,18 @@
 #include <atomic>
 #include "common.cuh"
 
-// per-Gaussian backward with the SH row kept in registers (see DirectIO) instead of staged through shared memory
-#ifndef GS2M_PB_DIRECT
-#define GS2M_PB_DIRECT 1
-#endif
-#ifndef GS2M_PB_DIRECT_BLOCKS
-#define GS2M_PB_DIRECT_BLOCKS 2      // minimum resident 256-thread blocks per SM the register allocation must allow
+// Gaussians (= threads) per block of the staged kernel.  The API's row ranges start at multiples of 256, which every value
+// that divides 256 satisfies.  Measured on B200, config 4: 256 threads 0.445 ms, 128 0.464 ms, 64 0.424 ms (a block walks
+// through load / compute / store phases separated by barriers; 19 KB blocks give 11 of them per SM to overlap those phases).
+#ifndef GS2M_PB_THREADS
+#define GS2M_PB_THREADS 64
 #endif
 
 namespace gs2m {
 namespace {
+
+constexpr int PBT = GS2M_PB_THREADS;
+static_assert(256 % PBT == 0 && PBT % 32 == 0, "block size must divide 256");
 
 // accumulate mode adds with fire-and-forget vector reductions (red.global.add.v4.f32): the read-modify-write happens in
 // L2, so the store phase of a block has no load latency to wait for
@@ -362,14 +364,14 @@ struct GlobalIO : AccPolicy<MODE> {
 // ---- sink 2: rows of a shared staging area (M <= 16); the block copies them out coalesced ----
 constexpr int ST_SH = 48, ST_FEAT = 10, ST_COV = 6, ST_V3 = 3;
 struct StageSmem {
-    float sh[256 * (ST_SH + 1)];    // SH coefficients on the way in, dL/dsh on the way out; row stride (3*M)|1 (odd:
+    float sh[PBT * (ST_SH + 1)];    // SH coefficients on the way in, dL/dsh on the way out; row stride (3*M)|1 (odd:
                                     // conflict-free when every thread walks its own row)
-    float feat[256 * ST_FEAT];
-    float cov[256 * ST_COV];
-    float mean3d[256 * ST_V3];
-    float scale[256 * ST_V3];
-    float color[256 * ST_V3];
-    unsigned char vis[256];         // row visibility: accumulate mode skips the rows of culled Gaussians
+    float feat[PBT * ST_FEAT];
+    float cov[PBT * ST_COV];
+    float mean3d[PBT * ST_V3];
+    float scale[PBT * ST_V3];
+    float color[PBT * ST_V3];
+    unsigned char vis[PBT];         // row visibility: accumulate mode skips the rows of culled Gaussians
 };
 template <int MODE>
 struct StagedIO : AccPolicy<MODE> {
@@ -398,46 +400,6 @@ struct StagedIO : AccPolicy<MODE> {
     __device__ void sh_out(int k, float v) { sm.sh[t * sh_row + k] = v; }
 };
 
-// ---- sink 3: like sink 2 for the short rows, but the SH row never goes through shared memory: the thread holds its own
-// 3*M floats in registers (128-bit loads of its contiguous row, all in flight at once), overwrites them in place with the
-// gradient and writes the row back with 128-bit stores / vector reductions.  Needs 3*M to be a multiple of 4 (M = 4, 8, 12, 16).
-// Shared memory drops from 76 KB to 26 KB per block, so that registers, not shared memory, bound the occupancy and the L1 keeps
-// the sectors two neighbouring 128-bit accesses of a thread share.
-struct SmallSmem {
-    float feat[256 * ST_FEAT];
-    float cov[256 * ST_COV];
-    float mean3d[256 * ST_V3];
-    float scale[256 * ST_V3];
-    float color[256 * ST_V3];
-    unsigned char vis[256];
-};
-template <int MODE>
-struct DirectIO : AccPolicy<MODE> {
-    using AccPolicy<MODE>::kAccOther;
-    static constexpr bool kAnyM = false;
-    const BwdParams& p; size_t i; SmallSmem& sm; int t; float (&shr)[ST_SH];
-    __device__ DirectIO(const BwdParams& p_, size_t i_, SmallSmem& sm_, int t_, float (&shr_)[ST_SH]) : p(p_), i(i_), sm(sm_), t(t_), shr(shr_) {}
-    __device__ void mean2d(float4 v) {
-        float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
-        if (kAccOther) red_add_f4(o, v);
-        else *o = v;
-    }
-    __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
-    __device__ void opacity(float v) { if (kAccOther) atomicAdd(p.dL_dopacity + i, v); else p.dL_dopacity[i] = v; }
-    __device__ void color(int k, float v) { sm.color[t * ST_V3 + k] = v; }
-    __device__ void feature(int k, float v) { sm.feat[t * ST_FEAT + k] = v; }
-    __device__ void mean3d(int k, float v) { sm.mean3d[t * ST_V3 + k] = v; }
-    __device__ void cov(int k, float v) { sm.cov[t * ST_COV + k] = v; }
-    __device__ void scale(int k, float v) { sm.scale[t * ST_V3 + k] = v; }
-    __device__ void rot(float4 v) {
-        float4* o = reinterpret_cast<float4*>(p.dL_drot) + i;
-        if (kAccOther) red_add_f4(o, v);
-        else *o = v;
-    }
-    __device__ float sh_in(int k) const { return shr[k]; }
-    __device__ void sh_out(int k, float v) { shr[k] = v; }      // k is a compile-time constant at every call site
-};
-
 // coalesced copy-out of `n` floats of the block's contiguous output region (16-byte aligned start)
 template <bool ACC, int ROW>
 __device__ __forceinline__ void block_store(float* __restrict__ dst, const float* __restrict__ src, int n,
@@ -445,7 +407,7 @@ __device__ __forceinline__ void block_store(float* __restrict__ dst, const float
     const int n4 = n >> 2;
     float4* d4 = reinterpret_cast<float4*>(dst);
     const float4* s4 = reinterpret_cast<const float4*>(src);
-    for (int e = threadIdx.x; e < n4; e += 256) {
+    for (int e = threadIdx.x; e < n4; e += PBT) {
         if (ACC && !(vis[(4 * e) / ROW] | vis[(4 * e + 3) / ROW])) continue;   // += 0 for culled rows: skip the RMW
         float4 v = s4[e];
         if (ACC) {
@@ -459,7 +421,7 @@ __device__ __forceinline__ void block_store(float* __restrict__ dst, const float
             d4[e] = v;
         }
     }
-    for (int e = (n4 << 2) + threadIdx.x; e < n; e += 256) {
+    for (int e = (n4 << 2) + threadIdx.x; e < n; e += PBT) {
         if (ACC) { if (vis[e / ROW]) atomicAdd(dst + e, src[e]); }
         else dst[e] = src[e];
     }
@@ -477,13 +439,13 @@ __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdPar
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
+__global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
     constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StageSmem& sm = *reinterpret_cast<StageSmem*>(smem_raw);
     const int t = threadIdx.x;
-    const size_t row0 = (size_t)p.row_begin + (size_t)blockIdx.x * 256;      // row_begin is a multiple of 256 (checked by the API)
-    const int rows = (int)min((size_t)256, (size_t)p.row_end - row0);
+    const size_t row0 = (size_t)p.row_begin + (size_t)blockIdx.x * PBT;      // row_begin is a multiple of 256 (checked by the API)
+    const int rows = (int)min((size_t)PBT, (size_t)p.row_end - row0);
     const int idx = (int)row0 + t;
     const bool inside = t < rows;
     const bool visible = inside && p.radii[idx] > 0;
@@ -497,7 +459,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         const float* __restrict__ src = p.shs + row0 * sh_row;
         const int n = rows * sh_row;
         if ((sh_row & 3) == 0) {      // 128-bit global loads; a float4 never straddles two rows
-            for (int e4 = t; e4 < (n >> 2); e4 += 256) {
+            for (int e4 = t; e4 < (n >> 2); e4 += PBT) {
                 const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
                 if (p.radii[row0 + r] > 0) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(src) + e4);
@@ -506,7 +468,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
                 }
             }
         } else {
-            for (int e = t; e < n; e += 256) {
+            for (int e = t; e < n; e += PBT) {
                 const int r = e / sh_row, c = e - r * sh_row;
                 if (p.radii[row0 + r] > 0) sm.sh[r * sh_pad + c] = __ldg(src + e);
             }
@@ -523,7 +485,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
         float* __restrict__ dst = p.dL_dsh + row0 * sh_row;
         const int n = rows * sh_row;
         if ((sh_row & 3) == 0) {
-            for (int e4 = t; e4 < (n >> 2); e4 += 256) {
+            for (int e4 = t; e4 < (n >> 2); e4 += PBT) {
                 const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
                 if (kAccParams && !sm.vis[r]) continue;
                 const float* q = sm.sh + r * sh_pad + c;
@@ -533,7 +495,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
                 else *d4 = v;
             }
         } else {
-            for (int e = t; e < n; e += 256) {
+            for (int e = t; e < n; e += PBT) {
                 const int r = e / sh_row, c = e - r * sh_row;
                 if (kAccParams && !sm.vis[r]) continue;
                 const float v = sm.sh[r * sh_pad + c];
@@ -548,69 +510,15 @@ __global__ void __launch_bounds__(256) preprocess_backward_staged_kernel(BwdPara
     if (p.dL_dcolor) block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256, GS2M_PB_DIRECT_BLOCKS) preprocess_backward_direct_kernel(BwdParams p, GeomState g) {
-    constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
-    __shared__ SmallSmem sm;
-    const int t = threadIdx.x;
-    const size_t row0 = (size_t)p.row_begin + (size_t)blockIdx.x * 256;
-    const int rows = (int)min((size_t)256, (size_t)p.row_end - row0);
-    const int idx = (int)row0 + t;
-    const bool inside = t < rows;
-    const bool visible = inside && p.radii[idx] > 0;
-    const int n4 = (3 * p.M) >> 2;                       // float4s per SH row (3*M is a multiple of 4 here)
-    float acc[GS2M_ACC_STRIDE];
-    load_acc_row(g, (size_t)(inside ? idx : 0), visible, acc);
-    float shr[ST_SH];
-    float4* __restrict__ sh_row_out = p.dL_dsh ? reinterpret_cast<float4*>(p.dL_dsh) + (size_t)idx * n4 : nullptr;
-    if (visible && p.shs != nullptr) {
-        const float4* __restrict__ src = reinterpret_cast<const float4*>(p.shs) + (size_t)idx * n4;
-#pragma unroll
-        for (int j = 0; j < ST_SH / 4; ++j) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < n4) v = __ldg(src + j);
-            shr[4 * j] = v.x; shr[4 * j + 1] = v.y; shr[4 * j + 2] = v.z; shr[4 * j + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < ST_SH; ++k) shr[k] = 0.f;
-    }
-    sm.vis[t] = visible ? 1 : 0;
-    if (inside) {
-        DirectIO<MODE> io(p, (size_t)idx, sm, t, shr);
-        gaussian_backward(p, g, idx, visible, acc, io);
-        // the thread's SH gradient row: one write per element (zeros for a culled Gaussian when overwriting; nothing when adding)
-        if (sh_row_out != nullptr && (visible || !kAccParams)) {
-#pragma unroll
-            for (int j = 0; j < ST_SH / 4; ++j) {
-                if (j < n4) {
-                    const float4 v = make_float4(shr[4 * j], shr[4 * j + 1], shr[4 * j + 2], shr[4 * j + 3]);
-                    if (kAccParams) red_add_f4(sh_row_out + j, v);
-                    else sh_row_out[j] = v;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    block_store<kAccOther, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
-    if (p.dL_dcov3D) block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
-    block_store<kAccParams, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
-    block_store<kAccOther, ST_V3>(p.dL_dscale + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
-    if (p.dL_dcolor) block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
-}
-
 }  // namespace
 
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
     if (p.P == 0 || p.row_end <= p.row_begin) return GS2M_OK;
-    const int blocks = (p.row_end - p.row_begin + 255) / 256;
+    const int blocks = (p.row_end - p.row_begin + 255) / 256;             // generic kernel: 256 threads
+    const int blocks_staged = (p.row_end - p.row_begin + PBT - 1) / PBT;
     count_launches(1);
     if (p.accumulate < 0 || p.accumulate > 2) { set_error("accumulate mode %d outside 0..2", p.accumulate); return GS2M_ERR_INVALID_ARGUMENT; }
-    if (GS2M_PB_DIRECT && p.M <= 16 && ((3 * p.M) & 3) == 0) {
-        if (p.accumulate == 1) preprocess_backward_direct_kernel<1><<<blocks, 256, 0, s>>>(p, g);
-        else if (p.accumulate == 2) preprocess_backward_direct_kernel<2><<<blocks, 256, 0, s>>>(p, g);
-        else preprocess_backward_direct_kernel<0><<<blocks, 256, 0, s>>>(p, g);
-    } else if (p.M <= 16) {
+    if (p.M <= 16) {
         static PerDeviceOnce configured;
         int dev;
         if (configured.need(dev)) {
@@ -619,9 +527,9 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
             GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
             configured.done(dev);
         }
-        if (p.accumulate == 1) preprocess_backward_staged_kernel<1><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
-        else if (p.accumulate == 2) preprocess_backward_staged_kernel<2><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
-        else preprocess_backward_staged_kernel<0><<<blocks, 256, sizeof(StageSmem), s>>>(p, g);
+        if (p.accumulate == 1) preprocess_backward_staged_kernel<1><<<blocks_staged, PBT, sizeof(StageSmem), s>>>(p, g);
+        else if (p.accumulate == 2) preprocess_backward_staged_kernel<2><<<blocks_staged, PBT, sizeof(StageSmem), s>>>(p, g);
+        else preprocess_backward_staged_kernel<0><<<blocks_staged, PBT, sizeof(StageSmem), s>>>(p, g);
     } else {
         if (p.accumulate == 1) preprocess_backward_generic_kernel<1><<<blocks, 256, 0, s>>>(p, g);
         else if (p.accumulate == 2) preprocess_backward_generic_kernel<2><<<blocks, 256, 0, s>>>(p, g);

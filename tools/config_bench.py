@@ -49,6 +49,8 @@ def time_impl(mod, cfg, F, n_views, iters, warmup, device):
             scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None, features=feats[v])
 
     def iteration():
+        for t in list(leaves.values()) + feats + [m2d]:
+            t.grad = None                                       # optimizer.zero_grad(set_to_none=True), train.py:259
         for v in range(n_views):
             color, radii, observe, buffer = fwd(v)
             torch.autograd.backward([color, buffer], [gc, gb])
