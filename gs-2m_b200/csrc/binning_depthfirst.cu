@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(CS_THREADS) compact_spine_kernel(uint2* __rest
     }
     if (!CONTROL) return;
     __syncthreads();
-    atomicAdd(&s_total, wide);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wide += __shfl_down_sync(0xffffffffu, wide, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_total, wide);
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned long long R64 = s_total;
