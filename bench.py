@@ -95,7 +95,7 @@ class ClockSampler:
 
 def build_workload(cfg, n_views_total, my_views, device):
     """Replicated scene + this rank's cameras/features, all resident on `device`."""
-    scene = syn.scene_to(syn.make_scene(cfg["P"], shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
+    scene = syn.scene_to(syn.make_scene(cfg["P"], shell_fraction=cfg["shell"], cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap")), device)
     cams_cpu = syn.make_cameras(n_views_total, cfg["W"], cfg["H"], radius=cfg["cam_radius"])
     cams = {v: syn.camera_to(cams_cpu[v], device) for v in my_views}
     feats = {v: syn.pack_features(scene, cams[v], cfg["F"]) for v in my_views}
@@ -114,7 +114,7 @@ def run_ours(args, cfg, rank, world, device):
     V_per = args.views_per_rank
     n_views = world * V_per
     my_views = list(vp.shard_views(n_views, world, rank))
-    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap")), device)
     cams_cpu = syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])
     cams = {v: syn.camera_to(cams_cpu[v], device) for v in range(n_views)}       # all views: dp_check replays the whole batch
     settings = {v: syn.raster_settings_for(cams[v], F, dgr.GaussianRasterizationSettings) for v in range(n_views)}
@@ -297,24 +297,34 @@ def run_ours(args, cfg, rank, world, device):
         seq_step = holder["step"] = make_step(begin_view, world_=1, rank_=0, n_streams=1, buckets=step.buckets)
         seq_step.run(n_views, reduce=False)
         torch.cuda.synchronize(device)
-        errs = {}
-        for k in vp.ParameterBuckets.names:
-            d = (got[k].double() - step.buckets.tensors[k].double()).abs().max()
-            errs[k] = float(d / step.buckets.tensors[k].double().abs().max().clamp_min(1e-30))
+        seq = {k: t.clone() for k, t in step.buckets.tensors.items()}
+        seq_step.run(n_views, reduce=False)          # the same sequential sum once more: this rank's own run-to-run noise
+        torch.cuda.synchronize(device)
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        ill = ("scaling", "rotation")   # fed by the ill-conditioned conic backward: order-of-summation noise of ~1e-3
+        errs = {k: rel(got[k], seq[k]) for k in vp.ParameterBuckets.names}
+        noise = {k: rel(step.buckets.tensors[k], seq[k]) for k in vp.ParameterBuckets.names}
         checksum = torch.stack([t.view(torch.int32).to(torch.int64).sum() for t in got.values()]).sum().reshape(1)
         sums = [torch.zeros_like(checksum) for _ in range(world)]
         dist.all_gather(sums, checksum)
-        worst = torch.tensor([max(v for k, v in errs.items() if k not in ("scaling", "rotation")),
-                              max(errs["scaling"], errs["rotation"])], device=device, dtype=torch.float64)
+        worst = torch.tensor([max(v for k, v in errs.items() if k not in ill), max(errs[k] for k in ill),
+                              max(noise[k] for k in ill), max(v for k, v in noise.items() if k not in ill)],
+                             device=device, dtype=torch.float64)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         identical = all(int(x) == int(sums[0]) for x in sums)
-        dp_check = {"views": n_views, "max_rel_err_vs_sequential_sum": float(worst[0]),
-                    "max_rel_err_ill_conditioned(scaling,rotation)": float(worst[1]),
+        well, ill_err, ill_noise, well_noise = (float(x) for x in worst)
+        dp_check = {"views": n_views, "max_rel_err_vs_sequential_sum": well,
+                    "max_rel_err_ill_conditioned(scaling,rotation)": ill_err,
+                    "sequential_run_to_run_noise": {"well_conditioned": well_noise, "scaling,rotation": ill_noise},
                     "ranks_bit_identical": identical,
-                    "pass": bool(float(worst[0]) <= 1e-4 and float(worst[1]) <= 2e-3 and identical),
+                    "pass": bool(well <= 1e-4 and ill_err <= max(2e-3, 4.0 * ill_noise) and identical),
                     "what": "all-reduced raw-parameter gradients of one step on every rank vs the same rank running all %d views "
-                            "sequentially (max|d|/max|ref| per group, max over groups and ranks; 1e-4, and 2e-3 for the "
-                            "ill-conditioned scaling/rotation pair whose single-GPU run-to-run noise is ~3e-4)" % n_views}
+                            "sequentially (max|d|/max|ref| per group, max over groups and ranks).  Gate: 1e-4; for the "
+                            "scaling/rotation pair, which the ill-conditioned conic backward feeds, max(2e-3, 4 x the noise "
+                            "between two sequential runs on the same rank)" % n_views}
+        del seq
         del got
         if not dp_check["pass"] and rank == 0:
             print("dp_check FAILED: %s" % json.dumps(dp_check), file=sys.stderr)
@@ -463,7 +473,7 @@ def cpu_baseline(cfg, args, budget_tiles=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     P, W, H, F = cfg["P"], cfg["W"], cfg["H"], cfg["F"]
-    scene = syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"))
+    scene = syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap"))
     cam = syn.make_cameras(1, W, H, radius=cfg["cam_radius"])[0]
     feats = syn.pack_features(scene, cam, F)
     gc, gb = syn.make_upstream_grads(W, H, F)

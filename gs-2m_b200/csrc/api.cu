@@ -98,6 +98,7 @@ size_t ImageState::carve(char* base, int W, int H, ImageState* out) {
     carve_array(p, im.final_T, n);
     carve_array(p, im.n_contrib, n);
     carve_array(p, im.ranges, tiles);
+    carve_array(p, im.tile_order, tiles);
     carve_array(p, im.bin_info, BIN_WORDS);
     if (out) *out = im;
     return (size_t)(p - base) + 128;
@@ -351,6 +352,8 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         rc = launch_identify_tile_ranges(0, b.keys_sorted, im.ranges, n_tiles, s);
         if (rc != GS2M_OK) return rc;
     }
+    { StageTimer t(GS2M_STAGE_RANGES, s); rc = launch_tile_order(n_tiles, im.ranges, im.tile_order, s); }
+    if (rc != GS2M_OK) return rc;
     { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
       rc = launch_blend_forward(p, g, point_list, b.masks, im, a->out_color, a->out_observe, a->out_buffer, s); }
     if (rc != GS2M_OK) return rc;

@@ -159,8 +159,8 @@ static_assert(BLEND_WARPS % BWD_CTA_WARPS == 0, "CTA must hold a divisor of the 
 #endif
 template <int F>
 __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
-    int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
+    const uint8_t* __restrict__ masks, int W, int H, int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ grad_color, const float* __restrict__ grad_buffer,
     float* __restrict__ grad_acc) {
@@ -171,7 +171,8 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     const int lane = threadIdx.x & 31;
     const int warp = (int)(blockIdx.x % BWD_CTAS_PER_TILE) * BWD_CTA_WARPS + (int)(threadIdx.x >> 5);   // warp block in the tile
     WarpSmemB<F>& sm = reinterpret_cast<WarpSmemB<F>*>(smem_raw)[threadIdx.x >> 5];
-    const int tile_x = blockIdx.x / BWD_CTAS_PER_TILE, tile_y = blockIdx.y;
+    const int tile = (int)tile_order[blockIdx.x / BWD_CTAS_PER_TILE];      // CTAs take the tiles longest list first
+    const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
     int px, py;
     pixel_of_thread(tile_x, tile_y, warp * 32 + lane, px, py);
     const bool inside = (px < W) && (py < H);
@@ -179,7 +180,7 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     const size_t N = (size_t)W * H;
     const size_t pix = (size_t)py * W + px;
 
-    const uint2 range = ranges[tile_y * tiles_x + tile_x];
+    const uint2 range = ranges[tile];
     const int n_list = (int)(range.y - range.x);
 
     // per-pixel state
@@ -340,7 +341,7 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
 template <int F>
 int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
              cudaStream_t s) {
-    dim3 grid(p.tiles_x * BWD_CTAS_PER_TILE, p.tiles_y);
+    const unsigned grid = (unsigned)(p.tiles_x * p.tiles_y) * BWD_CTAS_PER_TILE;
     const size_t smem = sizeof(WarpSmemB<F>) * BWD_CTA_WARPS;
     static PerDeviceOnce configured;   // per kernel instantiation and per device; callers may use several host threads
     int dev;
@@ -352,7 +353,7 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
         configured.done(dev);
     }
     count_launches(1);
-    blend_backward_kernel<F><<<grid, BWD_CTA_WARPS * 32, smem, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
+    blend_backward_kernel<F><<<grid, BWD_CTA_WARPS * 32, smem, s>>>(im.ranges, im.tile_order, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                                g.conic_c_opac, g.rgb, p.features, p.background,
                                                                im.final_T, im.n_contrib, p.grad_color, p.grad_buffer,
                                                                g.grad_acc);

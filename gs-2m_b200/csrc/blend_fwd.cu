@@ -39,8 +39,8 @@ static_assert(BLEND_WARPS % FWD_CTA_WARPS == 0, "CTA must hold a divisor of the 
 
 template <int F>
 __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_CTA_WARPS) blend_forward_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const uint8_t* __restrict__ masks, int W, int H,
-    int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
+    const uint8_t* __restrict__ masks, int W, int H, int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
     float* __restrict__ out_buffer) {
@@ -50,13 +50,14 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_C
     const int lane = threadIdx.x & 31;
     const int warp = (int)(blockIdx.x % FWD_CTAS_PER_TILE) * FWD_CTA_WARPS + (int)(threadIdx.x >> 5);   // warp block in the tile
     WarpSmemF<F>& sm = sm_all[threadIdx.x >> 5];
-    const int tile_x = blockIdx.x / FWD_CTAS_PER_TILE, tile_y = blockIdx.y;
+    const int tile = (int)tile_order[blockIdx.x / FWD_CTAS_PER_TILE];      // CTAs take the tiles longest list first
+    const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
     int px, py;
     pixel_of_thread(tile_x, tile_y, warp * 32 + lane, px, py);
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
 
-    const uint2 range = ranges[tile_y * tiles_x + tile_x];
+    const uint2 range = ranges[tile];
     const int n_list = (int)(range.y - range.x);
 
     bool done = !inside;
@@ -183,9 +184,9 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_C
 template <int F>
 int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
              float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
-    dim3 grid(p.tiles_x * FWD_CTAS_PER_TILE, p.tiles_y);
+    const unsigned grid = (unsigned)(p.tiles_x * p.tiles_y) * FWD_CTAS_PER_TILE;
     count_launches(1);
-    blend_forward_kernel<F><<<grid, FWD_CTA_WARPS * 32, 0, s>>>(im.ranges, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
+    blend_forward_kernel<F><<<grid, FWD_CTA_WARPS * 32, 0, s>>>(im.ranges, im.tile_order, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
                                                            g.conic_c_opac, g.rgb, p.features, p.background, im.final_T,
                                                            im.n_contrib, out_color, out_observe, out_buffer);
     GS2M_CUDA(cudaGetLastError());

@@ -52,6 +52,7 @@ struct ImageState {
     float*    final_T;        // [N]
     uint32_t* n_contrib;      // [N]
     uint2*    ranges;         // [tiles]
+    uint32_t* tile_order;     // [tiles] tile ids, longest lists first: the order in which the blend kernels' CTAs take the tiles
     uint32_t* bin_info;       // [8] control block written on the device: BIN_* indices below
     static size_t carve(char* base, int W, int H, ImageState* out);
 };
@@ -116,6 +117,7 @@ int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals
                        cudaStream_t s);
 int binning_df_emit(int V_cap, const uint32_t* n_ptr, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x,
                     int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
+int launch_tile_order(int n_tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s);
 int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
                          const ImageState& im, float* out_color, int* out_observe, float* out_buffer, cudaStream_t s);
 

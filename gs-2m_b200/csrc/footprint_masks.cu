@@ -67,7 +67,40 @@ __global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R_cap, const 
     }
 }
 
+// Longest lists first.  The blend kernels' CTAs take the tiles in this order (the hardware starts CTAs in index order), so the
+// tiles that run longest start first and the short ones fill in behind them.  It matters when list lengths are very unequal AND
+// pixels do not saturate early (e.g. after GS-2M's periodic opacity reset to 0.01, when every pixel walks its whole list):
+// a 292x-the-mean list that starts in the middle of the grid would otherwise finish long after everything else.  Exact order
+// is not needed: tiles are bucketed by the bit length of their list length (one CTA, a 33-bin counting sort).
+__global__ void __launch_bounds__(1024) tile_order_kernel(int n_tiles, const uint2* __restrict__ ranges,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_count[33], s_start[33];
+    if (threadIdx.x < 33) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        atomicAdd(&s_count[32 - __clz(r.y - r.x)], 1u);       // bucket = bit length of the list length (0 for an empty tile)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 32; b >= 0; --b) { s_start[b] = run; run += s_count[b]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        order[atomicAdd(&s_start[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)t;
+    }
+}
+
 }  // namespace
+
+int launch_tile_order(int n_tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s) {
+    count_launches(1);
+    tile_order_kernel<<<1, 1024, 0, s>>>(n_tiles, ranges, tile_order);
+    GS2M_CUDA(cudaGetLastError());
+    return GS2M_OK;
+}
 
 int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* keys_sorted, const uint32_t* point_list,
                             const GeomState& g, uint2* ranges, uint8_t* masks, cudaStream_t s) {

@@ -23,6 +23,10 @@ CONFIGS = {
     # load-imbalance probe (not a BASELINE config): 40 % of the Gaussians in a tight blob at the origin, so that a few dozen
     # tiles carry lists more than ten times the mean length
     "clustered-1m": dict(P=1_000_000, W=1959, H=1090, F=10, views=8, cam_radius=2.2, shell=0.0, cluster=(0.4, 0.02)),
+    # the same scene right after GS-2M's periodic opacity reset (scene/gaussian_model.py reset_opacity: min(opacity, 0.01)):
+    # no pixel saturates, every pixel walks its whole tile list, so the longest lists decide when the blend kernels finish
+    "clustered-1m-reset": dict(P=1_000_000, W=1959, H=1090, F=10, views=8, cam_radius=2.2, shell=0.0, cluster=(0.4, 0.02),
+                               opacity_cap=0.01),
 }
 
 
@@ -47,7 +51,7 @@ class Camera(NamedTuple):
     camera_center: torch.Tensor         # (3,)
 
 
-def make_scene(P, seed=SCENE_SEED, shell_fraction=0.0, extent=1.0, cluster=None):
+def make_scene(P, seed=SCENE_SEED, shell_fraction=0.0, extent=1.0, cluster=None, opacity_cap=None):
     """``cluster = (fraction, sigma)``: that fraction of the Gaussians (taken from the end of the arrays) is moved into an
     isotropic normal blob of that standard deviation around the origin (a dense object in a sparse scene)."""
     g = torch.Generator().manual_seed(seed)
@@ -76,6 +80,8 @@ def make_scene(P, seed=SCENE_SEED, shell_fraction=0.0, extent=1.0, cluster=None)
         n_cl = int(P * cluster[0])
         if n_cl > 0:
             means[P - n_cl:] = cluster[1] * torch.randn(n_cl, 3, generator=g)
+    if opacity_cap is not None:
+        opacities = opacities.clamp(max=opacity_cap)
     return Scene(means.float(), scales.float(), rotations.float(), opacities.float(), shs.float(), albedo.float(),
                  roughness.float(), metallic.float())
 

@@ -55,8 +55,9 @@ def decode_reference_buffers(P, W, H, R, geom, binning, img):
     return out
 
 
-def make_view(P, W, H, F, shell=0.0, cam_radius=3.0, view=0, n_views=1, device="cuda", scene_seed=syn.SCENE_SEED, cluster=None):
-    scene = syn.make_scene(P, seed=scene_seed, shell_fraction=shell, cluster=cluster)
+def make_view(P, W, H, F, shell=0.0, cam_radius=3.0, view=0, n_views=1, device="cuda", scene_seed=syn.SCENE_SEED, cluster=None,
+              opacity_cap=None):
+    scene = syn.make_scene(P, seed=scene_seed, shell_fraction=shell, cluster=cluster, opacity_cap=opacity_cap)
     cams = syn.make_cameras(max(n_views, view + 1), W, H, radius=cam_radius)
     cam = cams[view]
     feats = syn.pack_features(scene, cam, F)

@@ -102,7 +102,7 @@ def _free_port():
 @pytest.mark.parametrize("n_views,param_buckets,deferred", [(5, False, False), (1, False, False), (5, True, False),
                                                             (5, False, True), (1, True, True), (5, True, True)])
 def test_two_rank_step_equals_sequential_sum(tmp_path, n_views, param_buckets, deferred):
-    world, P, M = 2, (700 if deferred else 37), 4          # 700 Gaussians: three 256-aligned ranges in the deferred step
+    world, P, M = 2, (1500 if deferred else 37), 4         # 1500 Gaussians: three 256-aligned, shrinking ranges in the deferred step
     mp.spawn(_worker, args=(world, _free_port(), n_views, P, M, str(tmp_path), param_buckets, deferred), nprocs=world, join=True)
     res = [torch.load(os.path.join(tmp_path, "rank%d.pt" % r)) for r in range(world)]
     assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(n_views))

@@ -34,7 +34,7 @@ def make_leaves(scene):
 
 def time_impl(mod, cfg, F, n_views, iters, warmup, device):
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
-    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap")), device)
     cams = [syn.camera_to(c, device) for c in syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])]
     feats = [syn.pack_features(scene, c, F).requires_grad_(True) for c in cams]
     gc, gb = [t.to(device) for t in syn.make_upstream_grads(W, H, F)]
@@ -91,7 +91,7 @@ def time_graphed(dgr, cfg, F, n_views, iters, device):
     replayed: what the kernels cost without Python, ctypes and per-kernel launch overhead (fixed shapes; the camera matrices
     live in static buffers a caller would refresh with three tiny copies)."""
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
-    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster")), device)
+    scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap")), device)
     cams = [syn.camera_to(c, device) for c in syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])]
     feats = [syn.pack_features(scene, c, F) for c in cams]
     gc, gb = [t.to(device) for t in syn.make_upstream_grads(W, H, F)]

@@ -17,7 +17,7 @@ cfg_name = sys.argv[1] if len(sys.argv) > 1 else "tnt-3m"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 cfg = syn.CONFIGS[cfg_name]
 scene, cam, feats, gc, gb = helpers.make_view(cfg["P"], cfg["W"], cfg["H"], cfg["F"], shell=cfg["shell"], cam_radius=cfg["cam_radius"],
-                                              cluster=cfg.get("cluster"))
+                                              cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap"))
 lib = _native.load()
 for _ in range(3):
     helpers.run_ours(dgr, scene, cam, feats, cfg["F"], gc, gb)
