@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(256) ranges_and_masks_kernel(int R_cap, const 
 // tiles that run longest start first and the short ones fill in behind them.  It matters when list lengths are very unequal AND
 // pixels do not saturate early (e.g. after GS-2M's periodic opacity reset to 0.01, when every pixel walks its whole list):
 // a 292x-the-mean list that starts in the middle of the grid would otherwise finish long after everything else.  Exact order
-// is not needed: tiles are bucketed by the bit length of their list length (one CTA, a 33-bin counting sort).
+// is not needed: tiles are bucketed by the bit length of their list length (one CTA, a 33-bin counting sort, 13 us).
+// Measured against row-major order (B200, blend forward / backward): DTU-shaped 300 k scene (lists up to 5.5x the mean)
+// 0.172 / 0.253 -> 0.138 / 0.214 ms; clustered scene after an opacity reset 2.74 / 2.78 -> 2.66 / 2.57 ms; uniform 3 M scene
+// 1.116 / 1.893 -> 1.099 / 1.883 ms.
 __global__ void __launch_bounds__(1024) tile_order_kernel(int n_tiles, const uint2* __restrict__ ranges,
                                                           uint32_t* __restrict__ order) {
     __shared__ uint32_t s_count[33], s_start[33];

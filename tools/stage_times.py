@@ -29,9 +29,9 @@ for _ in range(iters):
 torch.cuda.synchronize()
 st = _native.profile_read()
 tot = 0.0
-for k, (ms, n) in st.items():
-    print("%-16s %8.4f ms" % (k, ms / max(n, 1)))
-    tot += ms / max(n, 1)
+for k, (ms, n) in st.items():      # per VIEW (a stage may bracket several kernels / be entered twice per view, e.g. the two sorts)
+    print("%-16s %8.4f ms   (%d brackets per view)" % (k, ms / iters, n // iters))
+    tot += ms / iters
 print("%-16s %8.4f ms" % ("sum", tot))
 o = helpers.run_ours(dgr, scene, cam, feats, cfg["F"])
 ln = (o["ranges"][:, 1] - o["ranges"][:, 0]).float()
