@@ -142,14 +142,17 @@ def run_ours(args, cfg, rank, world, device):
 
     def finish_view(h, buckets, accumulate, rows):
         st = h["st"]
+        # (the packing chain of the view's camera runs inside the per-Gaussian kernel: gs2m_backward_args::chain)
         dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, h["s"], h["q"], None, h["f"], h["radii"], st, h["state"],
                          grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows,
-                         densify_stats=holder["step"].stats.backward_args())
-        buckets.chain_rows(raw, st.viewmatrix, st.campos, h["radii"], rows[0], rows[1], blend_metallic=blend_metallic)
+                         densify_stats=holder["step"].stats.backward_args(),
+                         chain=buckets.chain_spec(raw, blend_metallic=blend_metallic))
 
     def make_step(begin, world_=world, rank_=rank, n_streams=args.streams, buckets=None):
-        return vp.ViewShardedStep(P, M, device, world=world_, rank=rank_, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
-                                  begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets)
+        st_ = vp.ViewShardedStep(P, M, device, world=world_, rank=rank_, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
+                                 begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets)
+        st_.buckets.fused_chain = True
+        return st_
 
     step = holder["step"] = make_step(begin_view)
 

@@ -381,8 +381,20 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     }
     // dL_dcolor / dL_dcov3D are the gradients of the PRECOMPUTED colour / covariance inputs: required when those inputs are
     // used, optional (NULL = not written) when SHs / scale+rotation are
-    if (!a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dmeans3D || !a->dL_dscale || !a->dL_drot || !a->dL_dfeatures ||
-        (a->colors_precomp && !a->dL_dcolor) || (a->cov3D_precomp && !a->dL_dcov3D) || (a->M > 0 && a->shs && !a->dL_dsh)) {
+    const gs2m_param_chain* ch = a->chain;
+    if (ch) {
+        if (!a->scales || !a->rotations || a->M > 16 || a->accumulate == 1) {
+            set_error("backward: chain needs scales + rotations inputs, M <= 16 and accumulate 0 or 2"); return GS2M_ERR_INVALID_ARGUMENT;
+        }
+        if (!ch->scaling_raw || !ch->rotation_raw || !ch->opacity_raw || !ch->albedo_raw || !ch->roughness_raw || !ch->metallic_raw ||
+            !ch->d_xyz || !ch->d_scaling_raw || !ch->d_rotation_raw || !ch->d_opacity_raw || !ch->d_albedo_raw ||
+            !ch->d_roughness_raw || !ch->d_metallic_raw || !a->cam_pos) {
+            set_error("backward: chain with a NULL pointer"); return GS2M_ERR_INVALID_ARGUMENT;
+        }
+    } else if (!a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dmeans3D || !a->dL_dscale || !a->dL_drot || !a->dL_dfeatures) {
+        set_error("backward: missing gradient output pointer"); return GS2M_ERR_INVALID_ARGUMENT;
+    }
+    if ((a->colors_precomp && !a->dL_dcolor) || (a->cov3D_precomp && !a->dL_dcov3D) || (a->M > 0 && a->shs && !a->dL_dsh)) {
         set_error("backward: missing gradient output pointer"); return GS2M_ERR_INVALID_ARGUMENT;
     }
     if (a->R < 0) { set_error("backward: negative R"); return GS2M_ERR_INVALID_ARGUMENT; }
@@ -421,6 +433,8 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     p.row_end = ranged ? a->row_end : a->P;
     p.densify_grad_accum = a->densify_grad_accum; p.densify_grad_accum_abs = a->densify_grad_accum_abs;
     p.densify_denom = a->densify_denom;
+    p.has_chain = ch != nullptr;
+    if (ch) p.chain = *ch; else memset(&p.chain, 0, sizeof(p.chain));
 
     GeomState g;
     GeomState::carve(a->geometry_buffer, p.P, &g);

@@ -134,6 +134,8 @@ struct BwdParams {
     int accumulate;
     int row_begin, row_end;                                                // Gaussians the per-Gaussian stage covers
     float *densify_grad_accum, *densify_grad_accum_abs, *densify_denom;   // optional (nullptr = off)
+    bool has_chain;                                                        // chain the gradients through the packing stage
+    gs2m_param_chain chain;
 };
 int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
                           const ImageState& im, cudaStream_t s);

@@ -14,6 +14,7 @@
 // tensors are updated with += instead (several views summed before one all-reduce).
 #include <atomic>
 #include "common.cuh"
+#include "pack_math.cuh"
 
 // Gaussians (= threads) per block of the staged kernel.  The API's row ranges start at multiples of 256, which every value
 // that divides 256 satisfies.  Measured on B200, config 4: 256 threads 0.445 ms, 128 0.464 ms, 64 0.424 ms (a block walks
@@ -380,6 +381,7 @@ struct StagedIO : AccPolicy<MODE> {
     const BwdParams& p; size_t i; StageSmem& sm; int t; int sh_row;
     __device__ StagedIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
     __device__ void mean2d(float4 v) {
+        if (p.dL_dmeans2D == nullptr) return;       // (optional in chain mode)
         float4* o = reinterpret_cast<float4*>(p.dL_dmeans2D) + i;
         if (kAccOther) red_add_f4(o, v);
         else *o = v;
@@ -400,6 +402,22 @@ struct StagedIO : AccPolicy<MODE> {
     __device__ void sh_out(int k, float v) { sm.sh[t * sh_row + k] = v; }
 };
 
+// ---- sink 3: sink 2 for dL/dsh, dL/dmeans2D and the optional precomputed-input gradients; the gradients w.r.t. the activated
+// scale / rotation / opacity, the feature columns and the 3-D mean stay in registers and are chained through the caller-side
+// packing stage (pack_math.cuh) before anything is written: what leaves the kernel are raw-parameter gradients
+// (gs2m_backward_args::chain).  Saves the 72 B/Gaussian scratch round trip and a separate chain kernel per view.
+template <int MODE>
+struct ChainIO : StagedIO<MODE> {
+    float g_scale[3], g_feat[GS2M_NUM_FEATURES], g_mean[3], g_opac;
+    float4 g_rot;
+    __device__ ChainIO(const BwdParams& p_, size_t i_, StageSmem& sm_, int t_) : StagedIO<MODE>(p_, i_, sm_, t_) {}
+    __device__ void opacity(float v) { g_opac = v; }
+    __device__ void feature(int k, float v) { g_feat[k] = v; }
+    __device__ void mean3d(int k, float v) { g_mean[k] = v; }
+    __device__ void scale(int k, float v) { g_scale[k] = v; }
+    __device__ void rot(float4 v) { g_rot = v; }
+};
+
 // coalesced copy-out of `n` floats of the block's contiguous output region (16-byte aligned start)
 template <bool ACC, int ROW>
 __device__ __forceinline__ void block_store(float* __restrict__ dst, const float* __restrict__ src, int n,
@@ -408,7 +426,8 @@ __device__ __forceinline__ void block_store(float* __restrict__ dst, const float
     float4* d4 = reinterpret_cast<float4*>(dst);
     const float4* s4 = reinterpret_cast<const float4*>(src);
     for (int e = threadIdx.x; e < n4; e += PBT) {
-        if (ACC && !(vis[(4 * e) / ROW] | vis[(4 * e + 3) / ROW])) continue;   // += 0 for culled rows: skip the RMW
+        if (ACC && !(vis[(4 * e) / ROW] | vis[(4 * e + 1) / ROW] | vis[(4 * e + 2) / ROW] | vis[(4 * e + 3) / ROW]))
+            continue;                                                           // += 0 for culled rows: skip the RMW
         float4 v = s4[e];
         if (ACC) {
             // rows of culled Gaussians hold no staged values in accumulate mode: mask them out element-wise
@@ -438,7 +457,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdPar
     gaussian_backward(p, g, idx, visible, acc, io);
 }
 
-template <int MODE>
+template <int MODE, bool CHAIN>
 __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
     constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -476,9 +495,41 @@ __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdPara
         __syncthreads();
     }
     sm.vis[t] = visible ? 1 : 0;
+    float* const s_scalar = sm.feat;      // chain mode: the feature staging is unused; it carries three [PBT] scalar columns
     if (inside) {
-        StagedIO<MODE> io(p, (size_t)idx, sm, t);
-        gaussian_backward(p, g, idx, visible, acc, io);
+        if (CHAIN) {
+            ChainIO<MODE> io(p, (size_t)idx, sm, t);
+            gaussian_backward(p, g, idx, visible, acc, io);
+            RawGrads r;
+            float mean[3] = {0.f, 0.f, 0.f};
+            if (visible) {
+                const PackIn in{p.P, p.means3D, p.chain.scaling_raw, p.chain.rotation_raw, p.chain.opacity_raw, p.chain.albedo_raw,
+                                p.chain.roughness_raw, p.chain.metallic_raw, p.viewmatrix, p.cam_pos, p.chain.z_depth,
+                                p.chain.blend_metallic};
+                const Derived d = derive(in, idx);
+                r = pack_chain(in, idx, d, io.g_scale, io.g_rot, io.g_opac, io.g_feat);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) mean[k] = io.g_mean[k] + r.dp[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { r.dscaling[k] = 0.f; r.dalbedo[k] = 0.f; }
+                r.drot = make_float4(0.f, 0.f, 0.f, 0.f);
+                r.dopacity = r.droughness = r.dmetallic = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sm.mean3d[t * ST_V3 + k] = mean[k];
+                sm.scale[t * ST_V3 + k] = r.dscaling[k];
+                sm.color[t * ST_V3 + k] = r.dalbedo[k];
+            }
+            s_scalar[t] = r.dopacity; s_scalar[PBT + t] = r.droughness; s_scalar[2 * PBT + t] = r.dmetallic;
+            float4* o = reinterpret_cast<float4*>(p.chain.d_rotation_raw) + idx;
+            if (kAccParams) { if (visible) red_add_f4(o, r.drot); }
+            else *o = r.drot;
+        } else {
+            StagedIO<MODE> io(p, (size_t)idx, sm, t);
+            gaussian_backward(p, g, idx, visible, acc, io);
+        }
     }
     __syncthreads();
     if (p.dL_dsh && sh_row > 0) {
@@ -503,6 +554,16 @@ __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdPara
             }
         }
     }
+    if (CHAIN) {      // raw-parameter gradients: overwritten (MODE 0) or added for the visible rows (MODE 2)
+        block_store<kAccParams, ST_V3>(p.chain.d_xyz + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
+        block_store<kAccParams, ST_V3>(p.chain.d_scaling_raw + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
+        block_store<kAccParams, ST_V3>(p.chain.d_albedo_raw + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
+        block_store<kAccParams, 1>(p.chain.d_opacity_raw + row0, s_scalar, rows, sm.vis);
+        block_store<kAccParams, 1>(p.chain.d_roughness_raw + row0, s_scalar + PBT, rows, sm.vis);
+        block_store<kAccParams, 1>(p.chain.d_metallic_raw + row0, s_scalar + 2 * PBT, rows, sm.vis);
+        if (p.dL_dcov3D) block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
+        return;
+    }
     block_store<kAccOther, ST_FEAT>(p.dL_dfeatures + row0 * ST_FEAT, sm.feat, rows * ST_FEAT, sm.vis);
     if (p.dL_dcov3D) block_store<kAccOther, ST_COV>(p.dL_dcov3D + row0 * ST_COV, sm.cov, rows * ST_COV, sm.vis);
     block_store<kAccParams, ST_V3>(p.dL_dmeans3D + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
@@ -522,15 +583,21 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
         static PerDeviceOnce configured;
         int dev;
         if (configured.need(dev)) {
-            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
-            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
-            GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)));
+#define GS2M_PB_ATTR(MODE, CHAIN) GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_staged_kernel<MODE, CHAIN>, \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem)))
+            GS2M_PB_ATTR(0, false); GS2M_PB_ATTR(1, false); GS2M_PB_ATTR(2, false); GS2M_PB_ATTR(0, true); GS2M_PB_ATTR(2, true);
+#undef GS2M_PB_ATTR
             configured.done(dev);
         }
-        if (p.accumulate == 1) preprocess_backward_staged_kernel<1><<<blocks_staged, PBT, sizeof(StageSmem), s>>>(p, g);
-        else if (p.accumulate == 2) preprocess_backward_staged_kernel<2><<<blocks_staged, PBT, sizeof(StageSmem), s>>>(p, g);
-        else preprocess_backward_staged_kernel<0><<<blocks_staged, PBT, sizeof(StageSmem), s>>>(p, g);
+        const size_t smem = sizeof(StageSmem);
+        if (p.has_chain) {
+            if (p.accumulate == 2) preprocess_backward_staged_kernel<2, true><<<blocks_staged, PBT, smem, s>>>(p, g);
+            else preprocess_backward_staged_kernel<0, true><<<blocks_staged, PBT, smem, s>>>(p, g);
+        } else if (p.accumulate == 1) preprocess_backward_staged_kernel<1, false><<<blocks_staged, PBT, smem, s>>>(p, g);
+        else if (p.accumulate == 2) preprocess_backward_staged_kernel<2, false><<<blocks_staged, PBT, smem, s>>>(p, g);
+        else preprocess_backward_staged_kernel<0, false><<<blocks_staged, PBT, smem, s>>>(p, g);
     } else {
+        if (p.has_chain) { set_error("chain mode needs M <= 16"); return GS2M_ERR_INVALID_ARGUMENT; }
         if (p.accumulate == 1) preprocess_backward_generic_kernel<1><<<blocks, 256, 0, s>>>(p, g);
         else if (p.accumulate == 2) preprocess_backward_generic_kernel<2><<<blocks, 256, 0, s>>>(p, g);
         else preprocess_backward_generic_kernel<0><<<blocks, 256, 0, s>>>(p, g);

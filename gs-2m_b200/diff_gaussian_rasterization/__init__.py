@@ -221,7 +221,7 @@ def alloc_grads(P, M, device, zero=False, skip=()):
 
 def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features,
                  radii, raster_settings: GaussianRasterizationSettings, state: RasterState, grads=None,
-                 accumulate=False, densify_stats=None, phase="all", rows=None):
+                 accumulate=False, densify_stats=None, phase="all", rows=None, chain=None):
     """Run the backward pipeline into ``grads`` (dict from :func:`alloc_grads`; allocated when None).
     With ``accumulate=True`` (or 1) the nine caller-visible tensors are updated with ``+=``; with ``accumulate=2`` only
     ``dL_dmeans3D`` and ``dL_dsh`` (GS-2M's raw, view-independent parameters) are, the rest is overwritten.
@@ -229,7 +229,11 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
     None) are updated like ``GaussianModel.add_densification_stats`` with this view's screen-space gradient.
     ``phase``: "all" (default), "blend" (only the reverse blend, which fills the state's internal accumulator) or "gaussians"
     (only the per-Gaussian stage, for Gaussians ``rows = (begin, end)`` when given; ``begin`` a multiple of 256) — a view-sharded
-    step runs "blend" per view and defers "gaussians" range by range so that finished ranges can be all-reduced early."""
+    step runs "blend" per view and defers "gaussians" range by range so that finished ranges can be all-reduced early.
+    ``chain = {"raw": {scaling, rotation, opacity, albedo, roughness, metallic}, "grads": {xyz, scaling, rotation, opacity, albedo,
+    roughness, metallic}, "z_depth": bool, "blend_metallic": bool}``: chain the gradients w.r.t. the activated scale / rotation /
+    opacity, the features and the 3-D mean through GS-2M's packing stage of this view's camera inside the kernel and add them to the
+    raw-parameter gradients in ``grads`` (``accumulate`` 0: overwritten, 2: ``+=``); ``grads["dL_dscale"]`` etc. may then be None."""
     lib = _native.load()
     dev = means3D.device
     rs = raster_settings
@@ -265,6 +269,8 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
             continue
         if t is None and (name == "dL_dconic" or (name == "dL_dcolor" and col_t is None) or (name == "dL_dcov3D" and cov_t is None)):
             continue
+        if t is None and chain is not None and name in ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dscale", "dL_drot", "dL_dfeatures"):
+            continue
         if t is None or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * c:
             raise RuntimeError("grads[%r] must be a contiguous float32 tensor with %d x %d elements on %s" % (name, P, c, dev))
     if P == 0:
@@ -295,6 +301,22 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
         b.dL_dsh = _ptr(grads["dL_dsh"]) if M > 0 else None
         b.accumulate = int(accumulate)
         b.stream = torch.cuda.current_stream(dev).cuda_stream
+        if chain is not None:
+            c = _native.ParamChain()
+            raw, out = chain["raw"], chain["grads"]
+            widths = {"xyz": 3, "scaling": 3, "rotation": 4, "opacity": 1, "albedo": 3, "roughness": 1, "metallic": 1}
+            for n in ("scaling", "rotation", "opacity", "albedo", "roughness", "metallic"):
+                t = raw[n]
+                if t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * widths[n]:
+                    raise RuntimeError("chain raw[%r] must be a contiguous float32 tensor with %d x %d elements on %s" % (n, P, widths[n], dev))
+                setattr(c, n + "_raw", t.data_ptr())
+            for n, w in widths.items():
+                t = out[n]
+                if t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * w:
+                    raise RuntimeError("chain grads[%r] must be a contiguous float32 tensor with %d x %d elements on %s" % (n, P, w, dev))
+                setattr(c, "d_xyz" if n == "xyz" else "d_" + n + "_raw", t.data_ptr())
+            c.z_depth, c.blend_metallic = int(bool(chain.get("z_depth", False))), int(bool(chain.get("blend_metallic", False)))
+            b.chain = _native.C.pointer(c)
         if densify_stats is not None:
             for t in densify_stats:
                 if t is not None and (t.dtype != torch.float32 or t.numel() != P or not t.is_contiguous() or t.device != dev):

@@ -39,6 +39,13 @@ class ForwardArgs(C.Structure):
     ]
 
 
+class ParamChain(C.Structure):
+    _fields_ = [("scaling_raw", _fp), ("rotation_raw", _fp), ("opacity_raw", _fp), ("albedo_raw", _fp), ("roughness_raw", _fp),
+                ("metallic_raw", _fp), ("z_depth", C.c_int), ("blend_metallic", C.c_int),
+                ("d_xyz", _fp), ("d_scaling_raw", _fp), ("d_rotation_raw", _fp), ("d_opacity_raw", _fp), ("d_albedo_raw", _fp),
+                ("d_roughness_raw", _fp), ("d_metallic_raw", _fp)]
+
+
 class BackwardArgs(C.Structure):
     _fields_ = [
         ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int), ("R_capacity", C.c_int),
@@ -61,6 +68,7 @@ class BackwardArgs(C.Structure):
         ("phase", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int),
         ("grad_acc_dirty", C.c_int),
         ("densify_grad_accum", _fp), ("densify_grad_accum_abs", _fp), ("densify_denom", _fp),
+        ("chain", C.POINTER(ParamChain)),
     ]
 
 

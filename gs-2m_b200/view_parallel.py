@@ -234,14 +234,22 @@ class ParameterBuckets:
             return []
         return _all_reduce_many([self.tensors[n][begin:end] for n in self.names], async_op)
 
+    fused_chain = False      # set when every view goes through ``chain_spec`` (the first view of a range then overwrites all groups)
+
     def begin_rows(self):
-        """Deferred step: the groups ``chain_view`` adds into start the step at zero (``xyz`` / ``sh`` are overwritten by the
-        first view's rasterizer backward)."""
-        self.flat[self._packed_from:].zero_()
+        """Deferred step: the groups ``chain_view`` / ``chain_rows`` add into start the step at zero (``xyz`` / ``sh`` are
+        overwritten by the first view's rasterizer backward); nothing to do when the kernel-side chain is used."""
+        if not self.fused_chain:
+            self.flat[self._packed_from:].zero_()
 
     def zero_rows(self, begin: int, end: int):
         for n in self.names:
             self.tensors[n][begin:end].zero_()
+
+    def chain_spec(self, raw: Dict[str, torch.Tensor], z_depth=False, blend_metallic=False) -> dict:
+        """``chain=`` argument of ``backward_raw``: the rasterizer's per-Gaussian backward then chains its gradients through the
+        packing stage of the view's camera itself and adds them to this bucket set (no scratch round trip, no ``chain_rows``)."""
+        return {"raw": raw, "grads": self.tensors, "z_depth": z_depth, "blend_metallic": blend_metallic}
 
     def chain_rows(self, raw: Dict[str, torch.Tensor], world_view_transform, camera_center, radii, begin: int, end: int,
                    z_depth=False, blend_metallic=False):

@@ -104,6 +104,19 @@ long long gs2m_last_instance_count(void);
 
 int gs2m_rasterize_forward(const gs2m_forward_args* args);
 
+/* Optional tail of the backward for GS-2M's training loop: chain the rasterizer's gradients w.r.t. the ACTIVATED scales /
+ * rotations / opacities and the 10 `features` columns straight through the caller-side packing stage of THIS view's camera
+ * (gs2m_pack_forward: scene/gaussian_model.py:113-172, gaussian_renderer/__init__.py:82-96) inside the per-Gaussian kernel, and
+ * add the result to the gradients of the RAW parameters.  Replaces writing dL_dscale / dL_drot / dL_dopacity / dL_dfeatures /
+ * dL_dmeans3D (which may then be NULL, like dL_dmeans2D) followed by gs2m_pack_backward_accumulate.  With accumulate = 0 every
+ * element of the seven raw-gradient tensors is overwritten (zeros for culled Gaussians); with accumulate = 2 they are updated
+ * with += for the visible Gaussians.  d_xyz receives dL_dmeans3D plus the position term of the distance / depth column. */
+typedef struct gs2m_param_chain {
+    const float *scaling_raw, *rotation_raw, *opacity_raw, *albedo_raw, *roughness_raw, *metallic_raw;   /* [P,3] [P,4] [P,1] [P,3] [P,1] [P,1] */
+    int z_depth, blend_metallic;
+    float *d_xyz, *d_scaling_raw, *d_rotation_raw, *d_opacity_raw, *d_albedo_raw, *d_roughness_raw, *d_metallic_raw;
+} gs2m_param_chain;
+
 /* ---- backward: replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:58-90, rasterizer_impl.cu:334-438) ---- */
 typedef struct gs2m_backward_args {
     int P, D, M, R;             /* R = value returned by forward */
@@ -164,6 +177,7 @@ typedef struct gs2m_backward_args {
     float* densify_grad_accum;
     float* densify_grad_accum_abs;
     float* densify_denom;
+    const gs2m_param_chain* chain;   /* optional, see above (needs scales + rotations inputs and M <= 16) */
 } gs2m_backward_args;
 
 int gs2m_rasterize_backward(const gs2m_backward_args* args);

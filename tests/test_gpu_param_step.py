@@ -11,8 +11,9 @@ import view_parallel as vp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_streams,deferred", [(1, False), (2, False), (1, True), (2, True)])
+@pytest.mark.parametrize("n_streams,deferred", [(1, False), (2, False), (1, True), (2, True), (1, "fused"), (2, "fused")])
 def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
+    """deferred = "fused": the packing chain runs inside the rasterizer's per-Gaussian backward (gs2m_backward_args::chain)."""
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization.packing import activate_and_pack
     P, W, H, F, M, n_views = 30_000, 320, 240, 10, 16, 4
@@ -63,6 +64,11 @@ def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
 
     def finish_view(h, buckets, accumulate, rows):
         cam, st = cams[h["v"]], settings[h["v"]]
+        if deferred == "fused":
+            dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, h["s"], h["q"], None, h["f"], h["radii"], st, h["state"],
+                             grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows,
+                             chain=buckets.chain_spec(raw, blend_metallic=True))
+            return
         dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, h["s"], h["q"], None, h["f"], h["radii"], st, h["state"],
                          grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows)
         buckets.chain_rows(raw, cam.world_view_transform, cam.camera_center, h["radii"], rows[0], rows[1], blend_metallic=True)
@@ -71,6 +77,7 @@ def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
         step = vp.ViewShardedStep(P, M, "cuda", world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
                                   begin_view=begin_view, finish_view=finish_view, n_chunks=5)
         assert len(step.chunks) == 5 and len(step.bucket_sets) == 1
+        step.buckets.fused_chain = deferred == "fused"
     else:
         step = vp.ViewShardedStep(P, M, "cuda", render_view, world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets)
     for b in step.bucket_sets:
