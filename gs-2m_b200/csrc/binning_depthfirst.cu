@@ -83,13 +83,25 @@ __global__ void __launch_bounds__(CS_THREADS) compact_spine_kernel(uint2* __rest
     const int n_tiles = (n + items_per_tile - 1) / items_per_tile;
     uint2 carry = make_uint2(0, 0);
     unsigned long long wide = 0ull;
-    for (int start = 0; start < n_tiles; start += CS_THREADS) {
-        const int i = start + threadIdx.x;
-        const uint2 v = (i < n_tiles) ? tile_sums[i] : make_uint2(0, 0);
-        wide += v.x;
+    constexpr int SP_ITEMS = 4;                 // consecutive tile sums per thread: a quarter of the block-scan rounds
+    for (int start = 0; start < n_tiles; start += CS_THREADS * SP_ITEMS) {
+        const int i0 = start + threadIdx.x * SP_ITEMS;
+        uint2 v[SP_ITEMS];
+        uint2 mine = make_uint2(0, 0);
+#pragma unroll
+        for (int k = 0; k < SP_ITEMS; ++k) {
+            v[k] = (i0 + k < n_tiles) ? tile_sums[i0 + k] : make_uint2(0, 0);
+            mine.x += v[k].x; mine.y += v[k].y;
+            wide += v[k].x;
+        }
         uint2 total;
-        const uint2 ex = block_exclusive_scan2(v, sw, total);
-        if (i < n_tiles) tile_sums[i] = make_uint2(carry.x + ex.x, carry.y + ex.y);
+        uint2 run = block_exclusive_scan2(mine, sw, total);
+        run.x += carry.x; run.y += carry.y;
+#pragma unroll
+        for (int k = 0; k < SP_ITEMS; ++k) {
+            if (i0 + k < n_tiles) tile_sums[i0 + k] = run;
+            run.x += v[k].x; run.y += v[k].y;
+        }
         carry.x += total.x; carry.y += total.y;
     }
     if (!CONTROL) return;
