@@ -41,12 +41,10 @@ constexpr int PARK_STRIDE = 33;  // padded row -> conflict-free for both write (
 
 template <int F>
 struct WarpSmemB {
-    static constexpr int NV = (3 + F + 3) / 4;
-    float4 a[32];                  // staged records of the current 32-entry step
-    float4 b[32];
-    float4 col[NV][32];
-    float4 dpix[2][16 * NV + 1];   // dL/d(colour,features) of the warp's 32 pixels, two 16-pixel halves (+16 B skew
-                                   // so that the two halves never share a bank in the reduce)
+    static constexpr int NV = StagedRing<F>::NV;
+    StagedRing<F> ring;            // staged records of the hits (blend_common.cuh)
+    float4 dpix[2][16 * NV + 1];   // dL/d(colour,features) of the warp's 32 pixels in the staged channel order, two 16-pixel
+                                   // halves (+16 B skew so that the two halves never share a bank in the reduce)
     float park_w[PARK * PARK_STRIDE];
     float park_q[PARK * PARK_STRIDE];
 };
@@ -83,23 +81,23 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
     if (e < n_parked) {
         const float4 ra = __ldg(rec_a + gid);
         const float4 rb = __ldg(rec_b + gid);
-        float gc[NC];
+        // colour / feature sums as aligned pairs: one FFMA2 per two channels (the 128-bit shared loads deliver the pairs)
+        constexpr int NP = StagedRing<F>::NPAIR;
+        float2 gc2[NP];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) gc[i] = 0.f;
+        for (int i = 0; i < NP; ++i) gc2[i] = make_float2(0.f, 0.f);
         const float* pw = &sm.park_w[e * PARK_STRIDE + h * 16];
         const float* pq = &sm.park_q[e * PARK_STRIDE + h * 16];
         const float4* dp = sm.dpix[h];
 #pragma unroll 8
         for (int j = 0; j < 16; ++j) {
-            const float w = pw[j];
-            float d[4 * NV];
+            const float2 ww = make_float2(pw[j], pw[j]);
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 const float4 t = dp[j * NV + k];
-                d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
+                if (2 * k < NP) gc2[2 * k] = fma2_rn(ww, make_float2(t.x, t.y), gc2[2 * k]);
+                if (2 * k + 1 < NP) gc2[2 * k + 1] = fma2_rn(ww, make_float2(t.z, t.w), gc2[2 * k + 1]);
             }
-#pragma unroll
-            for (int i = 0; i < NC; ++i) gc[i] = fmaf(w, d[i], gc[i]);
         }
         const float ca = ra.z, cb = ra.w, cc = rb.x, op = rb.y;
         const float gxr = ra.x - wpx0;                         // exact: both are multiples of ulp(mean) and the result is smaller
@@ -128,7 +126,7 @@ __device__ __forceinline__ void reduce_parked(WarpSmemB<F>& sm, int lane, int n_
         out[6] = -0.5f * op * myy;
         out[7] = m0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) out[8 + i] = gc[i];
+        for (int i = 0; i < NC; ++i) out[8 + i] = (staged_pos(i) & 1) ? gc2[staged_pos(i) >> 1].y : gc2[staged_pos(i) >> 1].x;
     }
 #pragma unroll
     for (int i = 0; i < NG; ++i) out[i] += __shfl_xor_sync(0xffffffffu, out[i], 16);
@@ -187,14 +185,14 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     const float T_final = inside ? final_T[pix] : 0.f;
     const uint32_t my_contrib = inside ? n_contrib[pix] : 0u;
     float T = T_final;
-    float dL[4 * NV];
+    float dL[4 * NV];              // staged channel order: colour 0..2, 0, features 4..
 #pragma unroll
     for (int i = 0; i < 4 * NV; ++i) dL[i] = 0.f;
     if (inside) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) dL[ch] = grad_color[ch * N + pix];
 #pragma unroll
-        for (int ch = 0; ch < F; ++ch) dL[3 + ch] = grad_buffer[ch * N + pix];
+        for (int ch = 0; ch < F; ++ch) dL[4 + ch] = grad_buffer[ch * N + pix];
     }
     const float bg_dot = bg[0] * dL[0] + bg[1] * dL[1] + bg[2] * dL[2];
 #pragma unroll
@@ -216,65 +214,58 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     float S = 0.f, last_alpha = 0.f, last_cd = 0.f;
     int n_parked = 0, my_gid = 0;
 
-    // software pipeline of the gathers (indices two steps ahead, records one step ahead)
-    // (the footprint masks written by the forward say which entries reach this warp's block; only those lanes gather)
+    // Software pipeline: list indices + footprint-mask bytes are fetched two steps ahead (registers), the records of the
+    // hits one step ahead (cp.async into the ring).  Lane l of step s looks at entry f = n_back-1-(32 s + l): back to front,
+    // lane 0 deepest.
     const uint32_t* __restrict__ list = point_list + range.x;
     const uint8_t* __restrict__ mlist = masks + range.x;
-    int gid_cur = (n_back - 1 - lane >= 0) ? (int)list[n_back - 1 - lane] : 0;
-    int gid_nxt = (n_back - 33 - lane >= 0) ? (int)list[n_back - 33 - lane] : 0;
-    bool hit_cur = (n_back - 1 - lane >= 0) && ((mlist[n_back - 1 - lane] >> warp) & 1);
-    uint32_t m_nxt = (n_back - 33 - lane >= 0) ? mlist[n_back - 33 - lane] : 0u;
-    float4 ra_cur = make_float4(0.f, 0.f, 0.f, 0.f), rb_cur = ra_cur;
-    if (hit_cur) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
+    StagedRing<F>& ring = sm.ring;
+    auto fetch = [&](int step, int& g, uint32_t& m) {
+        const int f = n_back - 1 - (32 * step + lane);
+        g = (f >= 0) ? (int)list[f] : 0;
+        m = (f >= 0) ? mlist[f] : 0u;
+    };
+    int gq[LIST_AHEAD];            // gq[i], mq[i]: index and mask byte of this lane's entry in step (current + 1 + i)
+    uint32_t mq[LIST_AHEAD];
+    int tail = 0, h_cur;
+    {
+        int g0;
+        uint32_t m0;
+        fetch(0, g0, m0);
+#pragma unroll
+        for (int i = 0; i < LIST_AHEAD; ++i) fetch(1 + i, gq[i], mq[i]);
+        const bool hit = (m0 >> warp) & 1u;
+        const uint32_t word = __ballot_sync(0xffffffffu, hit);
+        h_cur = __popc(word);
+        stage_step<F>(ring, lane, hit, word, g0, n_back - 1 - lane, 0, rec_a, rec_b, rgb, features);
+    }
 
     for (int base = 0; base < n_back; base += 32) {
-        // ---- lane l looks at entry f = n_back-1-(base+l): back-to-front, lane 0 deepest ----
-        const int f = n_back - 1 - (base + lane);
-        const int gid = gid_cur;
-        const bool hit = hit_cur;
-        const float4 ra = ra_cur, rb = rb_cur;
-        gid_cur = gid_nxt;
-        hit_cur = (m_nxt >> warp) & 1u;
-        if (hit_cur) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
-        gid_nxt = (f - 64 >= 0) ? (int)list[f - 64] : 0;
-        m_nxt = (f - 64 >= 0) ? mlist[f - 64] : 0u;
-        {
-            if (hit) {
-                sm.a[lane] = ra;
-                sm.b[lane] = make_float4(rb.x, rb.y, __int_as_float(gid), 0.f);
-                const float4 c = __ldg(rgb + gid);
-                float v[4 * NV];
-                v[0] = c.x; v[1] = c.y; v[2] = c.z;
-#pragma unroll
-                for (int i = 3; i < 4 * NV; ++i) v[i] = 0.f;
-                if (F > 0) {
-                    const float2* f2 = reinterpret_cast<const float2*>(features + (size_t)gid * GS2M_NUM_FEATURES);
-#pragma unroll
-                    for (int i = 0; i < (F + 1) / 2; ++i) {
-                        const float2 t = __ldg(f2 + i);
-                        v[3 + 2 * i] = t.x;
-                        if (2 * i + 1 < F) v[3 + 2 * i + 1] = t.y;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NV; ++k) sm.col[k][lane] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-            }
+        // ---- issue the next step's records behind the current step's if the ring has room for both ----
+        const int f1 = n_back - 1 - (base + 32 + lane);
+        const int g1 = gq[0];
+        const bool hit1 = (mq[0] >> warp) & 1u;
+        const uint32_t word1 = __ballot_sync(0xffffffffu, hit1);
+        const int h1 = __popc(word1);
+        const bool fits = h_cur + h1 <= 32;
+        if (fits) {
+            stage_step<F>(ring, lane, hit1, word1, g1, f1, tail + h_cur, rec_a, rec_b, rgb, features);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        uint32_t word = __ballot_sync(0xffffffffu, hit);
         __syncwarp();
 
         // ---- evaluate (lane = pixel) / reduce (lane = parked entry) ----
         // Two list entries per iteration: their alpha evaluations (the long dependent chain with the expf) are
         // independent and written branch-free so the scheduler can interleave them; only the T / S recurrences and
         // the parking are sequential.
-        while (word != 0) {
-            const int slot0 = __ffs(word) - 1;
-            word &= word - 1;
-            const bool two = word != 0;
-            const int slot1 = two ? __ffs(word) - 1 : slot0;
-            if (two) word &= word - 1;
-            const float4 ra0 = sm.a[slot0], rb0 = sm.b[slot0];
-            const float4 ra1 = sm.a[slot1], rb1 = sm.b[slot1];
+        for (int k = 0; k < h_cur; k += 2) {
+            const int slot0 = (tail + k) & 31;
+            const bool two = k + 1 < h_cur;
+            const int slot1 = two ? ((tail + k + 1) & 31) : slot0;
+            const float4 ra0 = ring.a[slot0], rb0 = ring.b[slot0];
+            const float4 ra1 = ring.a[slot1], rb1 = ring.b[slot1];
             float G0, alpha0, G1, alpha1;
             bool v0, v1;
             {
@@ -282,8 +273,8 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
                 v0 = pair_alpha_nb(ra0.x, ra0.y, ra0.z, ra0.w, rb0.x, rb0.y, pxf, pyf, dx, dy, G0, alpha0);
                 v1 = pair_alpha_nb(ra1.x, ra1.y, ra1.z, ra1.w, rb1.x, rb1.y, pxf, pyf, dx, dy, G1, alpha1);
             }
-            v0 = v0 && ((uint32_t)(n_back - 1 - (base + slot0)) < my_contrib);
-            v1 = v1 && two && ((uint32_t)(n_back - 1 - (base + slot1)) < my_contrib);
+            v0 = v0 && ((uint32_t)__float_as_int(rb0.w) < my_contrib);
+            v1 = v1 && two && ((uint32_t)__float_as_int(rb1.w) < my_contrib);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const bool v = u ? v1 : v0;
@@ -302,15 +293,22 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
                     float inv_one_m_alpha = __frcp_approx(one_m_alpha);
                     inv_one_m_alpha = fmaf(inv_one_m_alpha, fmaf(-one_m_alpha, inv_one_m_alpha, 1.0f), inv_one_m_alpha);
                     T *= inv_one_m_alpha;
-                    float c[4 * NV];
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) {
-                        const float4 t = sm.col[k][slot];
-                        c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
-                    }
+                    // cd = <colour+features, dL/dpixel>, one sequential chain in channel order.  (Two interleaved partial
+                    // sums on FFMA2 pairs were measured: 0.7 % faster, but the different association moved the raw-parameter
+                    // gradients from 2e-6 to 1.2e-5 of the reference's, which also accumulates channel by channel —
+                    // backward.cu:546-560 — so the scalar chain stays.)  Staged words behind the last used channel are
+                    // not ours and are never multiplied.
                     float cd = 0.f;
 #pragma unroll
-                    for (int i = 0; i < NC; ++i) cd = fmaf(c[i], dL[i], cd);
+                    for (int kk = 0; kk < NV; ++kk) {
+                        const float4 t = ring.col[kk][slot];
+                        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int ch = kk == 0 ? q : 4 * kk - 1 + q;       // blended channel of this staged word
+                            if ((kk == 0 && q < 3) || (kk > 0 && ch < NC)) cd = fmaf(tv[q], dL[4 * kk + q], cd);
+                        }
+                    }
                     S = fmaf(last_alpha, last_cd - S, S);          // a_prev*cd_prev + (1-a_prev)*S
                     last_alpha = alpha;
                     last_cd = cd;
@@ -330,8 +328,15 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
                 }
             }
         }
-        __syncwarp();   // every lane is done reading this step's staged records
+        __syncwarp();   // every lane is done reading this step's slots
+        tail = (tail + h_cur) & 31;
+        if (!fits) stage_step<F>(ring, lane, hit1, word1, g1, f1, tail, rec_a, rec_b, rgb, features);
+        h_cur = h1;
+#pragma unroll
+        for (int i = 0; i + 1 < LIST_AHEAD; ++i) { gq[i] = gq[i + 1]; mq[i] = mq[i + 1]; }
+        fetch(base / 32 + 1 + LIST_AHEAD, gq[LIST_AHEAD - 1], mq[LIST_AHEAD - 1]);
     }
+    cp_async_wait<0>();   // no copy may still be in flight when the warp's shared memory is released
     if (n_parked > 0) {
         __syncwarp();
         reduce_parked<F>(sm, lane, n_parked, my_gid, rec_a, rec_b, wpx0, wpy0, half_w, half_h, grad_acc);

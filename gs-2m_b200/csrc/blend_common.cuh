@@ -17,6 +17,117 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int tid,
     py = tile_y * GS2M_TILE_Y + (warp >> 1) * WARP_PIX_Y + (lane >> 3);
 }
 
+// Packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 work on an aligned register pair and take ONE issue slot for two
+// IEEE round-to-nearest results, so each half is bit-identical to the scalar __fmaf_rn / __fmul_rn / __fadd_rn).  The blend
+// kernels are issue-bound, and their channel loops (colour + features: 13 values per pair) are where the pairs come for free:
+// the staged colour vectors arrive as 128-bit shared loads, i.e. already in aligned pairs.
+#ifndef GS2M_F32X2
+#define GS2M_F32X2 1
+#endif
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
+#if GS2M_F32X2
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+#else
+    return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+#if GS2M_F32X2
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#endif
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+#if GS2M_F32X2
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+#endif
+}
+
+// Asynchronous global -> shared copies (LDGSTS): the staging of a list step's records never passes through registers,
+// so it can be issued a whole step ahead of its use without raising the register budget.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Staged records of the blend kernels: a 32-slot ring per warp that holds only the list entries whose footprint mask has
+// the warp's bit set ("hits"), compacted in list order.  Slot layout:
+//   a   = (mean.x, mean.y, conic.a, conic.b)                    cp.async 16 B from the blend record
+//   b   = (conic.c, opacity | Gaussian index, list position)    cp.async 8 B + one 8-byte store by the owning lane
+//   col = (r, g, b, 0) | f0..f3 | f4..f7 | f8, f9, -, -          cp.async 16 B (rgb) + 8 B per feature pair
+// Channel i of the blended vector therefore sits at position i for the colour and 4 + i for feature i; the '-' words are
+// never read as a used channel.
+template <int F>
+struct StagedRing {
+    static constexpr int NV = 1 + (F + 3) / 4;   // float4s per staged colour + feature vector
+    static constexpr int NPAIR = 2 + (F + 1) / 2; // aligned channel pairs: (r,g) (b,0) (f0,f1) ...
+    float4 a[32];
+    float4 b[32];
+    float4 col[NV][32];
+};
+// position of blended channel ch (0..2 colour, 3.. features) inside the staged vector / the pair accumulators
+__host__ __device__ constexpr int staged_pos(int ch) { return ch < 3 ? ch : ch + 1; }
+
+// How many list steps of (index, mask byte) each lane keeps in flight in registers beyond the step being issued (measured on
+// config 4: 2 -> 1.028 / 1.796 ms forward / backward, 3 -> 1.063 / 1.800, 4 -> 1.068 / 1.805, 6 -> 1.048 / 1.881).
+#ifndef GS2M_LIST_AHEAD
+#define GS2M_LIST_AHEAD 2
+#endif
+constexpr int LIST_AHEAD = GS2M_LIST_AHEAD;
+
+// Issues the copies of one list step: lane l holds entry (gid, pos) of the step and `hit` says whether it is staged; `word`
+// is the ballot of `hit`; the hits go to slots slot_base, slot_base+1, ... (mod 32) in lane order.  Always commits one group
+// (possibly empty) so that every lane's group count stays in step.
+template <int F>
+__device__ __forceinline__ void stage_step(StagedRing<F>& sm, int lane, bool hit, uint32_t word, int gid, int pos, int slot_base,
+                                           const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
+                                           const float4* __restrict__ rgb, const float* __restrict__ features) {
+    if (hit) {
+        const int slot = (slot_base + __popc(word & ((1u << lane) - 1u))) & 31;
+        cp_async16(&sm.a[slot], rec_a + gid);
+        cp_async8(&sm.b[slot], rec_b + gid);
+        *reinterpret_cast<int2*>(&sm.b[slot].z) = make_int2(gid, pos);
+        cp_async16(&sm.col[0][slot], rgb + gid);
+        if (F > 0) {
+            const float* frow = features + (size_t)gid * GS2M_NUM_FEATURES;
+#pragma unroll
+            for (int i = 0; i < (F + 1) / 2; ++i)
+                cp_async8(reinterpret_cast<float2*>(&sm.col[1 + i / 2][slot]) + (i & 1), frow + 2 * i);
+        }
+    }
+    cp_async_commit();
+}
+
 // Per-pair evaluation, bit-identical to the reference's renderCUDA as compiled for sm_100
 // (cuda_rasterizer/forward.cu:325-339; SASS: dx*a, dy*c, dy*(dy*c), fma(dx, dx*a, .), dy*(dx*b), fma(., -0.5, -.),
 // accurate expf, min(0.99, o*E)).  Returns false when the pair is skipped (power > 0 or alpha < 1/255).

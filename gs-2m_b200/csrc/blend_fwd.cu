@@ -21,14 +21,6 @@
 namespace gs2m {
 namespace {
 
-template <int F>
-struct WarpSmemF {
-    static constexpr int NV = (3 + F + 3) / 4;  // float4s per staged colour+feature vector
-    float4 a[32];                               // mean.x, mean.y, conic.a, conic.b
-    float4 b[32];                               // conic.c, opacity, Gaussian index (bits), -
-    float4 col[NV][32];                         // r,g,b,f0 | f1..f4 | f5..f8 | f9,0,0,0
-};
-
 // Warps are autonomous, so the CTA is only a scheduling unit: a tile's 8 warp blocks are spread over 8 / GS2M_FWD_WARPS CTAs.
 #ifndef GS2M_FWD_WARPS
 #define GS2M_FWD_WARPS 1
@@ -38,18 +30,19 @@ constexpr int FWD_CTAS_PER_TILE = BLEND_WARPS / FWD_CTA_WARPS;
 static_assert(BLEND_WARPS % FWD_CTA_WARPS == 0, "CTA must hold a divisor of the tile's 8 warp blocks");
 
 template <int F>
-__global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_CTA_WARPS) blend_forward_kernel(
+__global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
     const uint8_t* __restrict__ masks, int W, int H, int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
     float* __restrict__ out_buffer) {
-    __shared__ WarpSmemF<F> sm_all[FWD_CTA_WARPS];
-    constexpr int NV = WarpSmemF<F>::NV;
+    __shared__ StagedRing<F> sm_all[FWD_CTA_WARPS];
+    constexpr int NV = StagedRing<F>::NV;
+    constexpr int NP = StagedRing<F>::NPAIR;
 
     const int lane = threadIdx.x & 31;
     const int warp = (int)(blockIdx.x % FWD_CTAS_PER_TILE) * FWD_CTA_WARPS + (int)(threadIdx.x >> 5);   // warp block in the tile
-    WarpSmemF<F>& sm = sm_all[threadIdx.x >> 5];
+    StagedRing<F>& sm = sm_all[threadIdx.x >> 5];
     const int tile = (int)tile_order[blockIdx.x / FWD_CTAS_PER_TILE];      // CTAs take the tiles longest list first
     const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
     int px, py;
@@ -63,68 +56,58 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_C
     bool done = !inside;
     float T = 1.0f;
     uint32_t last_contributor = 0;
-    float C[3] = {0.f, 0.f, 0.f};
-    float Fv[F > 0 ? F : 1];
+    // colour + feature accumulators as aligned pairs in the staged order (r,g) (b,-) (f0,f1) ...: one FMUL2 + one FFMA2 per
+    // pair of channels, each half rounding exactly like the reference's scalar fma(T, alpha * c, C)
+    float2 A[NP];
 #pragma unroll
-    for (int i = 0; i < (F > 0 ? F : 1); ++i) Fv[i] = 0.f;
+    for (int i = 0; i < NP; ++i) A[i] = make_float2(0.f, 0.f);
 
     bool warp_done = __all_sync(0xffffffffu, done);
-    // software pipeline of the gathers: indices are fetched two steps ahead, records one step ahead, so their
-    // latency is covered by the blending of the current step
-    // (the footprint masks say which entries reach this warp's block; only those lanes gather a record)
+    // Software pipeline: list indices + footprint-mask bytes are fetched two steps ahead (registers), the records of the
+    // hits one step ahead (cp.async into the ring), so both latencies are covered by the blending of the current step.
     const uint32_t* __restrict__ list = point_list + range.x;
     const uint8_t* __restrict__ mlist = masks + range.x;
-    int gid_cur = (lane < n_list) ? (int)list[lane] : 0;
-    int gid_nxt = (32 + lane < n_list) ? (int)list[32 + lane] : 0;
-    bool hit_cur = (lane < n_list) && ((mlist[lane] >> warp) & 1);
-    uint32_t m_nxt = (32 + lane < n_list) ? mlist[32 + lane] : 0u;
-    float4 ra_cur = make_float4(0.f, 0.f, 0.f, 0.f), rb_cur = ra_cur;
-    if (hit_cur) { ra_cur = __ldg(rec_a + gid_cur); rb_cur = __ldg(rec_b + gid_cur); }
+    auto fetch = [&](int step, int& g, uint32_t& m) {
+        const int li = 32 * step + lane;
+        g = (li < n_list) ? (int)list[li] : 0;
+        m = (li < n_list) ? mlist[li] : 0u;
+    };
+    int gq[LIST_AHEAD];            // gq[i], mq[i]: index and mask byte of this lane's entry in step (current + 1 + i)
+    uint32_t mq[LIST_AHEAD];
+    int tail = 0, h_cur;
+    {
+        int g0;
+        uint32_t m0;
+        fetch(0, g0, m0);
+#pragma unroll
+        for (int i = 0; i < LIST_AHEAD; ++i) fetch(1 + i, gq[i], mq[i]);
+        const bool hit = (m0 >> warp) & 1u;
+        const uint32_t word = __ballot_sync(0xffffffffu, hit);
+        h_cur = __popc(word);
+        stage_step<F>(sm, lane, hit, word, g0, lane, 0, rec_a, rec_b, rgb, features);
+    }
     for (int base = 0; base < n_list && !warp_done; base += 32) {
-        // ---- lane l holds list entry base+l ----
-        const int li = base + lane;
-        const int gid = gid_cur;
-        const bool hit = hit_cur;
-        const float4 ra = ra_cur, rb = rb_cur;
-        gid_cur = gid_nxt;
-        hit_cur = (m_nxt >> warp) & 1u;
-        if (hit_cur) { ra_cur = __ldg(rec_a + gid_nxt); rb_cur = __ldg(rec_b + gid_nxt); }
-        gid_nxt = (li + 64 < n_list) ? (int)list[li + 64] : 0;
-        m_nxt = (li + 64 < n_list) ? mlist[li + 64] : 0u;
-        {
-            if (hit) {
-                sm.a[lane] = ra;
-                sm.b[lane] = make_float4(rb.x, rb.y, __int_as_float(gid), 0.f);
-                const float4 c = __ldg(rgb + gid);
-                float v[4 * NV];
-                v[0] = c.x; v[1] = c.y; v[2] = c.z;
-#pragma unroll
-                for (int i = 3; i < 4 * NV; ++i) v[i] = 0.f;
-                if (F > 0) {
-                    const float2* f2 = reinterpret_cast<const float2*>(features + (size_t)gid * GS2M_NUM_FEATURES);
-#pragma unroll
-                    for (int i = 0; i < (F + 1) / 2; ++i) {
-                        const float2 t = __ldg(f2 + i);
-                        v[3 + 2 * i] = t.x;
-                        if (2 * i + 1 < F) v[3 + 2 * i + 1] = t.y;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NV; ++k) sm.col[k][lane] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-            }
+        // ---- issue the next step's records behind the current step's if the ring has room for both ----
+        const int g1 = gq[0];
+        const bool hit1 = (mq[0] >> warp) & 1u;
+        const uint32_t word1 = __ballot_sync(0xffffffffu, hit1);
+        const int h1 = __popc(word1);
+        const bool fits = h_cur + h1 <= 32;
+        if (fits) {
+            stage_step<F>(sm, lane, hit1, word1, g1, base + 32 + lane, tail + h_cur, rec_a, rec_b, rgb, features);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        uint32_t word = __ballot_sync(0xffffffffu, hit);
         __syncwarp();
 
-        // ---- blend the surviving entries in list order ----
+        // ---- blend the current step's hits in list order ----
         // two entries per iteration: both alpha evaluations are independent and branch-free (interleaved by the
         // scheduler); the blend itself stays strictly in list order
-        while (word != 0 && !warp_done) {
-            const int slot0 = __ffs(word) - 1;
-            word &= word - 1;
-            const bool two = word != 0;
-            const int slot1 = two ? __ffs(word) - 1 : slot0;
-            if (two) word &= word - 1;
+        for (int k = 0; k < h_cur && !warp_done; k += 2) {
+            const int slot0 = (tail + k) & 31;
+            const bool two = k + 1 < h_cur;
+            const int slot1 = two ? ((tail + k + 1) & 31) : slot0;
             const float4 ra0 = sm.a[slot0], rb0 = sm.b[slot0];
             const float4 ra1 = sm.a[slot1], rb1 = sm.b[slot1];
             float G0, alpha0, G1, alpha1;
@@ -146,19 +129,15 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_C
                     if (test_T < 0.0001f) {
                         done = true;
                     } else {
-                        float c[4 * NV];
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) {
-                            const float4 t = sm.col[k][slot];
-                            c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w;
+                        for (int kk = 0; kk < NV; ++kk) {
+                            const float4 t = sm.col[kk][slot];
+                            if (2 * kk < NP) A[2 * kk] = fma2_rn(make_float2(T, T), mul2_rn(make_float2(alpha, alpha), make_float2(t.x, t.y)), A[2 * kk]);
+                            if (2 * kk + 1 < NP) A[2 * kk + 1] = fma2_rn(make_float2(T, T), mul2_rn(make_float2(alpha, alpha), make_float2(t.z, t.w)), A[2 * kk + 1]);
                         }
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) C[ch] = __fmaf_rn(T, __fmul_rn(alpha, c[ch]), C[ch]);
-#pragma unroll
-                        for (int ch = 0; ch < F; ++ch) Fv[ch] = __fmaf_rn(T, __fmul_rn(alpha, c[3 + ch]), Fv[ch]);
                         obs = T > 0.5f;
                         T = test_T;
-                        last_contributor = (uint32_t)(base + slot) + 1u;
+                        last_contributor = (uint32_t)__float_as_int(u ? rb1.w : rb0.w) + 1u;
                     }
                 }
                 const uint32_t ob = __ballot_sync(0xffffffffu, obs);
@@ -166,8 +145,15 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_C
             }
             warp_done = __all_sync(0xffffffffu, done);
         }
-        __syncwarp();   // all lanes are done with this step's staged records
+        __syncwarp();   // all lanes are done with this step's slots
+        tail = (tail + h_cur) & 31;
+        if (!fits) stage_step<F>(sm, lane, hit1, word1, g1, base + 32 + lane, tail, rec_a, rec_b, rgb, features);
+        h_cur = h1;
+#pragma unroll
+        for (int i = 0; i + 1 < LIST_AHEAD; ++i) { gq[i] = gq[i + 1]; mq[i] = mq[i + 1]; }
+        fetch(base / 32 + 1 + LIST_AHEAD, gq[LIST_AHEAD - 1], mq[LIST_AHEAD - 1]);
     }
+    cp_async_wait<0>();   // no copy may still be in flight when the warp's shared memory is released
 
     if (inside) {
         const size_t N = (size_t)W * H;
@@ -175,9 +161,12 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, (F == 9 ? 28 : 32) / FWD_C
         final_T[pix] = T;
         n_contrib[pix] = last_contributor;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) out_color[ch * N + pix] = __fmaf_rn(T, bg[ch], C[ch]);
+        for (int ch = 0; ch < 3; ++ch) out_color[ch * N + pix] = __fmaf_rn(T, bg[ch], (ch & 1) ? A[ch >> 1].y : A[ch >> 1].x);
 #pragma unroll
-        for (int ch = 0; ch < GS2M_NUM_FEATURES; ++ch) out_buffer[ch * N + pix] = (ch < F) ? Fv[ch < F ? ch : 0] : 0.f;
+        for (int ch = 0; ch < GS2M_NUM_FEATURES; ++ch) {
+            const int i = ch < F ? staged_pos(3 + ch) : 0;
+            out_buffer[ch * N + pix] = (ch < F) ? ((i & 1) ? A[i >> 1].y : A[i >> 1].x) : 0.f;
+        }
     }
 }
 

@@ -117,15 +117,22 @@ def test_random_shapes_vs_reference(dgr, ref, P, W, H, F, rad, shell, scene_seed
     r = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
     o = helpers.run_ours(dgr, scene, cam, feats, F, gc, gb)
     assert_forward_bit_exact(o, r, P)
+    r2 = None
     for k in GRAD_NAMES:
         if float(r[k].abs().max()) == 0.0:
             assert float(o[k].abs().max()) == 0.0, k
             continue
         err, l2 = helpers.grad_errors(o[k], r[k])
         # with a handful of Gaussians the max norm is one Gaussian's own cancellation-heavy pixel sum (signed terms of either
-        # implementation's fp32 summation order): north_star's 1e-4 there, the tight gate from 1000 Gaussians on
-        well = WELL_TOL if P >= 1000 else GRAD_TOL
-        assert err <= (2e-3 if k in ILL_CONDITIONED else well), "%s: max %.3e l2 %.3e" % (k, err, l2)
+        # implementation's fp32 summation order, and the order of the reference's per-pixel atomics changes from run to run):
+        # north_star's 1e-4 there, widened to 4 x the reference's own run-to-run distance when that is larger; the tight
+        # gate from 1000 Gaussians on
+        well = WELL_TOL
+        if P < 1000:
+            if r2 is None:
+                r2 = helpers.run_reference(ref, scene, cam, feats, F, gc, gb)
+            well = max(GRAD_TOL, 4.0 * helpers.grad_errors(r2[k], r[k])[0])
+        assert err <= (2e-3 if k in ILL_CONDITIONED else well), "%s: max %.3e l2 %.3e (gate %.3e)" % (k, err, l2, well)
 
 
 def test_ill_conditioned_gradients_against_fp64(dgr, ref):
