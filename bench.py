@@ -148,9 +148,19 @@ def run_ours(args, cfg, rank, world, device):
                          densify_stats=holder["step"].stats.backward_args(),
                          chain=buckets.chain_spec(raw, blend_metallic=blend_metallic))
 
+    def finish_views(handles, buckets, rows):
+        # all of the rank's views for one Gaussian range in ONE pass (gs2m_rasterize_backward_views): each thread owns a
+        # Gaussian, sums the views that see it on chip and writes the 64 raw-gradient floats once
+        chain = buckets.chain_spec(raw, blend_metallic=blend_metallic)
+        dgr.backward_views_raw([dict(grad_color=gc, grad_buffer=gb, means3D=raw["xyz"], shs=scene.shs, scales=h["s"], rotations=h["q"],
+                                     features=h["f"], radii=h["radii"], raster_settings=h["st"], state=h["state"],
+                                     grads=buckets.raster, densify_stats=holder["step"].stats.backward_args(), chain=chain)
+                                for h in handles], rows=rows)
+
     def make_step(begin, world_=world, rank_=rank, n_streams=args.streams, buckets=None):
         st_ = vp.ViewShardedStep(P, M, device, world=world_, rank=rank_, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
-                                 begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets)
+                                 begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets,
+                                 finish_views=None if args.per_view_finish else finish_views)
         st_.buckets.fused_chain = True
         return st_
 
@@ -582,6 +592,8 @@ def main():
     ap.add_argument("--views-per-rank", type=int, default=8)
     ap.add_argument("--streams", type=int, default=2, help="views in flight per rank (CUDA streams)")
     ap.add_argument("--chunks", type=int, default=4, help="Gaussian ranges of the deferred per-Gaussian backward / all-reduce")
+    ap.add_argument("--per-view-finish", action="store_true",
+                    help="run the per-Gaussian backward once per view (round-2a protocol) instead of one multi-view pass per range")
     ap.add_argument("--cpu-tiles", type=int, default=96, help="tiles of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -369,12 +369,16 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
 
 long long gs2m_last_instance_count(void) { return g_last_R; }
 
-int gs2m_rasterize_backward(const gs2m_backward_args* a) {
+// Validates one backward call and assembles the kernels' view of it.  Returns GS2M_OK with `empty` set when there is nothing to do.
+struct BackwardCall { BwdParams p; GeomState g; BinState b; ImageState im; cudaStream_t s; bool empty; };
+
+static int assemble_backward(const gs2m_backward_args* a, BackwardCall& c) {
+    c.empty = false;
     if (!a) { set_error("null args"); return GS2M_ERR_INVALID_ARGUMENT; }
     int rc = validate_common(a->P, a->D, a->M, a->width, a->height, a->feature_count, a->means3D, a->shs, a->colors_precomp,
                              a->scales, a->rotations, a->cov3D_precomp, a->features, a->viewmatrix, a->projmatrix, a->cam_pos);
     if (rc != GS2M_OK) return rc;
-    if (a->P == 0) return GS2M_OK;
+    if (a->P == 0) { c.empty = true; return GS2M_OK; }
     if (!a->radii || !a->geometry_buffer || !a->binning_buffer || !a->image_buffer || !a->grad_color ||
         (a->feature_count > 0 && !a->grad_buffer) || !a->background) {
         set_error("backward: missing saved state / upstream gradient pointer"); return GS2M_ERR_INVALID_ARGUMENT;
@@ -412,9 +416,9 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
         a->image_bytes < ImageState::carve(nullptr, a->width, a->height, nullptr)) {
         set_error("backward: a saved arena is smaller than forward allocated it"); return GS2M_ERR_INVALID_ARGUMENT;
     }
-    cudaStream_t s = (cudaStream_t)a->stream;
+    c.s = (cudaStream_t)a->stream;
 
-    BwdParams p;
+    BwdParams& p = c.p;
     p.P = a->P; p.D = a->D; p.M = a->M; p.W = a->width; p.H = a->height; p.F = a->feature_count; p.R = a->R;
     p.tiles_x = (a->width + GS2M_TILE_X - 1) / GS2M_TILE_X;
     p.tiles_y = (a->height + GS2M_TILE_Y - 1) / GS2M_TILE_Y;
@@ -436,12 +440,21 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     p.has_chain = ch != nullptr;
     if (ch) p.chain = *ch; else memset(&p.chain, 0, sizeof(p.chain));
 
-    GeomState g;
-    GeomState::carve(a->geometry_buffer, p.P, &g);
-    BinState b;
-    BinState::carve(a->binning_buffer, R_carve, &b);
-    ImageState im;
-    ImageState::carve(a->image_buffer, p.W, p.H, &im);
+    GeomState::carve(a->geometry_buffer, p.P, &c.g);
+    BinState::carve(a->binning_buffer, R_carve, &c.b);
+    ImageState::carve(a->image_buffer, p.W, p.H, &c.im);
+    return GS2M_OK;
+}
+
+int gs2m_rasterize_backward(const gs2m_backward_args* a) {
+    BackwardCall c;
+    int rc = assemble_backward(a, c);
+    if (rc != GS2M_OK || c.empty) return rc;
+    const BwdParams& p = c.p;
+    const GeomState& g = c.g;
+    const BinState& b = c.b;
+    const ImageState& im = c.im;
+    cudaStream_t s = c.s;
     const uint32_t* point_list = b.point_list;
 
     // The accumulator rows of the visible Gaussians were zeroed by the forward (preprocess); a second backward over the same
@@ -456,6 +469,35 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
         rc = launch_preprocess_backward(p, g, s);
     }
     return rc;
+}
+
+// The per-Gaussian stage (phase 2) of several views in one pass: every thread owns one Gaussian, walks the views that see it,
+// sums their chained raw-parameter gradients in registers / shared memory and writes each output element once.
+int gs2m_rasterize_backward_views(const gs2m_backward_args* views, int n_views) {
+    if (!views || n_views <= 0) { set_error("backward_views: no views"); return GS2M_ERR_INVALID_ARGUMENT; }
+    std::vector<BackwardCall> calls((size_t)n_views);
+    for (int v = 0; v < n_views; ++v) {
+        const gs2m_backward_args* a = views + v;
+        int rc = assemble_backward(a, calls[v]);
+        if (rc != GS2M_OK) return rc;
+        if (calls[v].empty) return GS2M_OK;        // P == 0 (the same for every view, checked below for the others)
+        const gs2m_backward_args* f = views;
+        if (a->phase != 2 || !a->chain) { set_error("backward_views: every view needs phase 2 and a chain"); return GS2M_ERR_INVALID_ARGUMENT; }
+        if (a->dL_dcolor || a->dL_dcov3D || a->colors_precomp || a->cov3D_precomp) {
+            set_error("backward_views: precomputed colours / covariances are not supported"); return GS2M_ERR_INVALID_ARGUMENT;
+        }
+        if (a->P != f->P || a->M != f->M || a->D != f->D || a->means3D != f->means3D || a->shs != f->shs || a->dL_dsh != f->dL_dsh ||
+            a->row_begin != f->row_begin || a->row_end != f->row_end || a->stream != f->stream ||
+            a->scale_modifier != f->scale_modifier || memcmp(a->chain, f->chain, sizeof(gs2m_param_chain)) != 0) {
+            set_error("backward_views: the views must share the Gaussians, the row range, the stream and the chain"); return GS2M_ERR_INVALID_ARGUMENT;
+        }
+    }
+    if (calls[0].p.row_end <= calls[0].p.row_begin) return GS2M_OK;
+    StageTimer t(GS2M_STAGE_PREPROCESS_BWD, calls[0].s);
+    std::vector<BwdParams> ps((size_t)n_views);
+    std::vector<GeomState> gs((size_t)n_views);
+    for (int v = 0; v < n_views; ++v) { ps[v] = calls[v].p; gs[v] = calls[v].g; }
+    return launch_preprocess_backward_views(ps.data(), gs.data(), n_views, views->accumulate != 0, calls[0].s);
 }
 
 int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buffer, char* binning_buffer,

@@ -140,6 +140,8 @@ struct BwdParams {
 int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
                           const ImageState& im, cudaStream_t s);
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
+// per-Gaussian stage of n views in one pass (chain mode): outputs written once with the sum over the views (`accumulate`: added)
+int launch_preprocess_backward_views(const BwdParams* ps, const GeomState* gs, int n_views, bool accumulate, cudaStream_t s);
 
 size_t sort_temp_bytes(int n);
 int sort_pairs_u64(uint64_t* keys_in, uint64_t* keys_out, uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit,

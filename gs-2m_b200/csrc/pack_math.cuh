@@ -31,13 +31,14 @@ __device__ __forceinline__ void column_of_R(const float* q, int axis, float* c) 
     else { c[0] = 2.f * (x * z + r * y); c[1] = 2.f * (y * z - r * x); c[2] = 1.f - 2.f * (x * x + y * y); }
 }
 
-__device__ __forceinline__ Derived derive(const PackIn& in, int i) {
-    Derived d;
-    const float* W = in.wvt;
-    const float p[3] = {in.xyz[3 * i], in.xyz[3 * i + 1], in.xyz[3 * i + 2]};
+// derive() in two halves: what depends only on the Gaussian (activations, normalised quaternion, thinnest axis and its
+// rotation-matrix column) and what depends on the camera (flip towards the camera, camera-space normal / position, distance).
+// A caller that visits one Gaussian for several views (preprocess_bwd.cu, backward_views) runs the first half once.
+__device__ __forceinline__ void derive_gaussian(const PackIn& in, int i, Derived& d, float (&p)[3]) {
+    p[0] = __ldg(in.xyz + 3 * (size_t)i); p[1] = __ldg(in.xyz + 3 * (size_t)i + 1); p[2] = __ldg(in.xyz + 3 * (size_t)i + 2);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) d.s[k] = expf(in.scaling[3 * i + k]);
-    const float4 rq = *reinterpret_cast<const float4*>(in.rotation + 4 * (size_t)i);
+    for (int k = 0; k < 3; ++k) d.s[k] = expf(__ldg(in.scaling + 3 * (size_t)i + k));
+    const float4 rq = __ldg(reinterpret_cast<const float4*>(in.rotation + 4 * (size_t)i));
     d.nq = fmaxf(sqrtf(rq.x * rq.x + rq.y * rq.y + rq.z * rq.z + rq.w * rq.w), 1e-12f);   // F.normalize eps
     d.q[0] = rq.x / d.nq; d.q[1] = rq.y / d.nq; d.q[2] = rq.z / d.nq; d.q[3] = rq.w / d.nq;
     d.nqh = sqrtf(d.q[0] * d.q[0] + d.q[1] * d.q[1] + d.q[2] * d.q[2] + d.q[3] * d.q[3]);
@@ -47,6 +48,10 @@ __device__ __forceinline__ Derived derive(const PackIn& in, int i) {
     if (d.s[1] < d.s[d.axis]) d.axis = 1;       // first minimum, like torch.argmin
     if (d.s[2] < d.s[d.axis]) d.axis = 2;
     column_of_R(d.qh, d.axis, d.col);
+}
+
+__device__ __forceinline__ void derive_view(const PackIn& in, const float (&p)[3], Derived& d) {
+    const float* W = in.wvt;
     const float vd = d.col[0] * (in.campos[0] - p[0]) + d.col[1] * (in.campos[1] - p[1]) + d.col[2] * (in.campos[2] - p[2]);
     d.flip = vd < 0.0f;
     float m[3];
@@ -61,6 +66,13 @@ __device__ __forceinline__ Derived derive(const PackIn& in, int i) {
         d.camp[k] = p[0] * W[k] + p[1] * W[4 + k] + p[2] * W[8 + k] + W[12 + k];
     }
     d.u = d.camn[0] * d.camp[0] + d.camn[1] * d.camp[1] + d.camn[2] * d.camp[2];
+}
+
+__device__ __forceinline__ Derived derive(const PackIn& in, int i) {
+    Derived d;
+    float p[3];
+    derive_gaussian(in, i, d, p);
+    derive_view(in, p, d);
     return d;
 }
 
@@ -68,8 +80,29 @@ __device__ __forceinline__ Derived derive(const PackIn& in, int i) {
 // (gf) -> gradients w.r.t. the raw parameters.  `dp` is the extra position gradient through the distance / depth column.
 struct RawGrads { float dp[3], dscaling[3], dalbedo[3]; float4 drot; float dopacity, droughness, dmetallic; };
 
-__device__ __forceinline__ RawGrads pack_chain(const PackIn& in, int i, const Derived& d, const float* gs, float4 gq, float go,
-                                               const float* gf) {
+// d sigmoid / d raw of the six sigmoid-activated parameters: per Gaussian, the same for every view
+struct SigmoidSlopes { float albedo[3], opacity, roughness, metallic; };
+__device__ __forceinline__ SigmoidSlopes sigmoid_slopes(const PackIn& in, int i) {
+    SigmoidSlopes k;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = sigmoidf(__ldg(in.albedo + 3 * (size_t)i + c));
+        k.albedo[c] = a * (1.0f - a);
+    }
+    const float o = sigmoidf(__ldg(in.opacity + i));
+    k.opacity = o * (1.0f - o);
+    const float ro = sigmoidf(__ldg(in.roughness + i));
+    k.roughness = ro * (1.0f - ro);
+    const float me = sigmoidf(__ldg(in.metallic + i));
+    k.metallic = me * (1.0f - me);
+    return k;
+}
+
+// The gradients that arrive here are often tiny (a Gaussian that barely touches a view), and an IEEE division with a tiny or
+// subnormal numerator leaves the hardware's fast path for a ~100-instruction routine (measured: 40 % of the per-Gaussian
+// backward's instructions).  The three norms are O(1), so the adjoints multiply by their reciprocals instead.
+__device__ __forceinline__ RawGrads pack_chain(const PackIn& in, const Derived& d, const SigmoidSlopes& sl, const float* gs,
+                                               float4 gq, float go, const float* gf) {
     const float* W = in.wvt;
     RawGrads out;
     // distance / depth column
@@ -83,11 +116,12 @@ __device__ __forceinline__ RawGrads pack_chain(const PackIn& in, int i, const De
         dp[j] = du * Wcn + (in.z_depth ? gf[1] * W[4 * j + 2] : 0.0f);
     }
     // normalisation n = m / |m|, flip, column of R(qh)
+    const float inv_nm = 1.0f / d.nm, inv_nqh = 1.0f / d.nqh, inv_nq = 1.0f / d.nq;
     const float ndn = d.n[0] * dn[0] + d.n[1] * dn[1] + d.n[2] * dn[2];
     float dc[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float dm = (dn[k] - d.n[k] * ndn) / d.nm;
+        const float dm = (dn[k] - d.n[k] * ndn) * inv_nm;
         dc[k] = d.flip ? -dm : dm;
     }
     const float r = d.qh[0], x = d.qh[1], y = d.qh[2], z = d.qh[3];
@@ -110,27 +144,27 @@ __device__ __forceinline__ RawGrads pack_chain(const PackIn& in, int i, const De
     }
     // qh = q / |q|  (build_rotation), then add the rasterizer's gradient w.r.t. q, then q = raw / max(|raw|, eps)
     const float qd = d.qh[0] * dqh[0] + d.qh[1] * dqh[1] + d.qh[2] * dqh[2] + d.qh[3] * dqh[3];
-        float dq[4] = {(dqh[0] - d.qh[0] * qd) / d.nqh + gq.x, (dqh[1] - d.qh[1] * qd) / d.nqh + gq.y,
-                   (dqh[2] - d.qh[2] * qd) / d.nqh + gq.z, (dqh[3] - d.qh[3] * qd) / d.nqh + gq.w};
+    const float dq[4] = {(dqh[0] - d.qh[0] * qd) * inv_nqh + gq.x, (dqh[1] - d.qh[1] * qd) * inv_nqh + gq.y,
+                         (dqh[2] - d.qh[2] * qd) * inv_nqh + gq.z, (dqh[3] - d.qh[3] * qd) * inv_nqh + gq.w};
     const float qq = d.q[0] * dq[0] + d.q[1] * dq[1] + d.q[2] * dq[2] + d.q[3] * dq[3];
     const bool clamped = d.nq <= 1e-12f;   // F.normalize divides by the clamped norm: no projection term then
-    float4 dr = make_float4((dq[0] - (clamped ? 0.f : d.q[0] * qq)) / d.nq, (dq[1] - (clamped ? 0.f : d.q[1] * qq)) / d.nq,
-                            (dq[2] - (clamped ? 0.f : d.q[2] * qq)) / d.nq, (dq[3] - (clamped ? 0.f : d.q[3] * qq)) / d.nq);
-    out.drot = dr;
+    out.drot = make_float4((dq[0] - (clamped ? 0.f : d.q[0] * qq)) * inv_nq, (dq[1] - (clamped ? 0.f : d.q[1] * qq)) * inv_nq,
+                           (dq[2] - (clamped ? 0.f : d.q[2] * qq)) * inv_nq, (dq[3] - (clamped ? 0.f : d.q[3] * qq)) * inv_nq);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         out.dp[k] = dp[k];
         out.dscaling[k] = gs[k] * d.s[k];
-        const float a = sigmoidf(in.albedo[3 * (size_t)i + k]);
-        out.dalbedo[k] = gf[5 + k] * a * (1.0f - a);
+        out.dalbedo[k] = gf[5 + k] * sl.albedo[k];
     }
-    const float o = sigmoidf(in.opacity[i]);
-    out.dopacity = go * o * (1.0f - o);
-    const float ro = sigmoidf(in.roughness[i]);
-    out.droughness = gf[8] * ro * (1.0f - ro);
-    const float me = sigmoidf(in.metallic[i]);
-    out.dmetallic = in.blend_metallic ? gf[9] * me * (1.0f - me) : 0.0f;
+    out.dopacity = go * sl.opacity;
+    out.droughness = gf[8] * sl.roughness;
+    out.dmetallic = in.blend_metallic ? gf[9] * sl.metallic : 0.0f;
     return out;
+}
+
+__device__ __forceinline__ RawGrads pack_chain(const PackIn& in, int i, const Derived& d, const float* gs, float4 gq, float go,
+                                               const float* gf) {
+    return pack_chain(in, d, sigmoid_slopes(in, i), gs, gq, go, gf);
 }
 
 }  // namespace gs2m

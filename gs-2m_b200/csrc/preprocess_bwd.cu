@@ -12,6 +12,7 @@
 // Every element of every output tensor is written (zeros for culled Gaussians), so the caller never has to
 // zero-fill 344 B/Gaussian the way rasterize_points.cu:150-159 does.  With `accumulate` the nine user-visible
 // tensors are updated with += instead (several views summed before one all-reduce).
+#include <algorithm>
 #include <atomic>
 #include "common.cuh"
 #include "pack_math.cuh"
@@ -52,7 +53,7 @@ __device__ __forceinline__ void load_acc_row(const GeomState& g, size_t i, bool 
         const float4* a4 = reinterpret_cast<const float4*>(g.grad_acc + i * GS2M_ACC_STRIDE);
 #pragma unroll
         for (int k = 0; k < GS2M_ACC_STRIDE / 4; ++k) {
-            const float4 t = a4[k];
+            const float4 t = __ldg(a4 + k);
             acc[4 * k] = t.x; acc[4 * k + 1] = t.y; acc[4 * k + 2] = t.z; acc[4 * k + 3] = t.w;
         }
     } else {
@@ -61,9 +62,35 @@ __device__ __forceinline__ void load_acc_row(const GeomState& g, size_t i, bool 
     }
 }
 
+// Everything the per-Gaussian math reads from global memory for one (Gaussian, view), fetched in one burst through the
+// non-coherent path before any of it is used: the reductions and stores in the math (asm volatile with a memory clobber) would
+// otherwise pin each load right in front of its first use, and a thread would sit through four or five memory latencies per
+// Gaussian instead of one (ncu: long_scoreboard 56 % of the stall samples before this change).
+struct GaussianInputs {
+    float acc[GS2M_ACC_STRIDE];
+    float cov[6];
+    float3 mean, scale;
+    float4 rot;
+    uchar4 clamped;
+};
+__device__ __forceinline__ void load_gaussian_inputs(const BwdParams& p, const GeomState& g, size_t i, bool visible, GaussianInputs& in) {
+    load_acc_row(g, i, visible, in.acc);
+    if (!visible) return;
+    in.mean = make_float3(__ldg(p.means3D + 3 * i), __ldg(p.means3D + 3 * i + 1), __ldg(p.means3D + 3 * i + 2));
+    const float* cov3D = (p.cov3D_precomp ? p.cov3D_precomp : g.cov3D) + 6 * i;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) in.cov[k] = __ldg(cov3D + k);
+    in.clamped = (p.shs != nullptr) ? __ldg(reinterpret_cast<const uchar4*>(g.clamped) + i) : make_uchar4(0, 0, 0, 0);
+    if (p.scales != nullptr) {
+        in.rot = __ldg(reinterpret_cast<const float4*>(p.rotations + 4 * i));
+        in.scale = make_float3(__ldg(p.scales + 3 * i), __ldg(p.scales + 3 * i + 1), __ldg(p.scales + 3 * i + 2));
+    }
+}
+
 template <class IO>
-__device__ __forceinline__ void gaussian_backward(const BwdParams& p, const GeomState& g, const int idx, const bool visible,
-                                                  const float (&acc)[GS2M_ACC_STRIDE], IO& io) {
+__device__ __forceinline__ void gaussian_backward(const BwdParams& p, const int idx, const bool visible,
+                                                  const GaussianInputs& gin, IO& io) {
+    const float (&acc)[GS2M_ACC_STRIDE] = gin.acc;
     const size_t i = (size_t)idx;
     const int M = p.M;
 
@@ -104,7 +131,7 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 
     const float* __restrict__ vm = p.viewmatrix;
     const float* __restrict__ pm = p.projmatrix;
-    const float3 m = make_float3(p.means3D[3 * i], p.means3D[3 * i + 1], p.means3D[3 * i + 2]);
+    const float3 m = gin.mean;
 
     // =================== conic -> cov2D -> cov3D, mean (via the Jacobian) ===================
     // This block is numerically ill-conditioned (differences of large products), so the reference's own outputs
@@ -112,8 +139,7 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
     // To add nothing on top of that, every operation below uses explicit round-to-nearest intrinsics in exactly the
     // association order of the reference's computeCov2DCUDA as compiled for sm_100 (read from its SASS), so that
     // identical inputs give bit-identical outputs.
-    const float* cov3D = (p.cov3D_precomp ? p.cov3D_precomp : g.cov3D) + 6 * i;
-    const float c0 = cov3D[0], c1 = cov3D[1], c2 = cov3D[2], c3 = cov3D[3], c4 = cov3D[4], c5 = cov3D[5];
+    const float c0 = gin.cov[0], c1 = gin.cov[1], c2 = gin.cov[2], c3 = gin.cov[3], c4 = gin.cov[4], c5 = gin.cov[5];
     const float tz_v = __fadd_rn(__fmaf_rn(m.z, vm[10], __fmaf_rn(m.x, vm[2], __fmul_rn(m.y, vm[6]))), vm[14]);
     const float tx_v = __fadd_rn(__fmaf_rn(m.z, vm[8], __fmaf_rn(m.x, vm[0], __fmul_rn(m.y, vm[4]))), vm[12]);
     const float ty_v = __fadd_rn(__fmaf_rn(m.z, vm[9], __fmaf_rn(m.x, vm[1], __fmul_rn(m.y, vm[5]))), vm[13]);
@@ -207,10 +233,10 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 
     // =================== colour -> SH coefficients and view direction ===================
     if (p.shs != nullptr) {
-        const float3 d0 = make_float3(m.x - p.cam_pos[0], m.y - p.cam_pos[1], m.z - p.cam_pos[2]);
+        const float3 d0 = make_float3(m.x - __ldg(p.cam_pos), m.y - __ldg(p.cam_pos + 1), m.z - __ldg(p.cam_pos + 2));
         const float inv_len = 1.0f / sqrtf(dot(d0, d0));
         const float x = d0.x * inv_len, y = d0.y * inv_len, z = d0.z * inv_len;
-        const uchar4 cl = reinterpret_cast<const uchar4*>(g.clamped)[idx];
+        const uchar4 cl = gin.clamped;
         const float3 dRGB = make_float3(cl.x ? 0.f : acc[8], cl.y ? 0.f : acc[9], cl.z ? 0.f : acc[10]);
 
         // basis value B[k] and its gradient (Bx,By,Bz) w.r.t. the (unnormalised-treated) direction, per coefficient
@@ -285,10 +311,9 @@ __device__ __forceinline__ void gaussian_backward(const BwdParams& p, const Geom
 
     // =================== cov3D -> scale, rotation ===================
     if (p.scales != nullptr) {
-        const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * i);
+        const float4 q = gin.rot;
         const float r = q.x, x = q.y, y = q.z, z = q.w;
-        const float s0 = p.scale_modifier * p.scales[3 * i], s1 = p.scale_modifier * p.scales[3 * i + 1],
-                    s2 = p.scale_modifier * p.scales[3 * i + 2];
+        const float s0 = p.scale_modifier * gin.scale.x, s1 = p.scale_modifier * gin.scale.y, s2 = p.scale_modifier * gin.scale.z;
         // columns of the rotation matrix
         const float3 r0 = make_float3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + r * z), 2.f * (x * z - r * y));
         const float3 r1 = make_float3(2.f * (x * y - r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + r * x));
@@ -452,13 +477,13 @@ __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdPar
     if (idx >= p.row_end) return;
     GlobalIO<MODE> io(p, (size_t)idx);
     const bool visible = p.radii[idx] > 0;
-    float acc[GS2M_ACC_STRIDE];
-    load_acc_row(g, (size_t)idx, visible, acc);
-    gaussian_backward(p, g, idx, visible, acc, io);
+    GaussianInputs gin;
+    load_gaussian_inputs(p, g, (size_t)idx, visible, gin);
+    gaussian_backward(p, idx, visible, gin, io);
 }
 
 template <int MODE, bool CHAIN>
-__global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
+__global__ void __maxnreg__(88) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
     constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StageSmem& sm = *reinterpret_cast<StageSmem*>(smem_raw);
@@ -469,9 +494,9 @@ __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdPara
     const bool inside = t < rows;
     const bool visible = inside && p.radii[idx] > 0;
     const int sh_row = 3 * p.M;
-    // the thread's own accumulator row is requested first: its latency passes under the cooperative SH staging below
-    float acc[GS2M_ACC_STRIDE];
-    load_acc_row(g, (size_t)(inside ? idx : 0), visible, acc);
+    // the thread's own inputs are requested first: their latency passes under the cooperative SH staging below
+    GaussianInputs gin;
+    load_gaussian_inputs(p, g, (size_t)(inside ? idx : 0), visible, gin);
     // coalesced load of the SH rows of the block's visible Gaussians
     const int sh_pad = sh_row | 1;
     if (p.shs != nullptr) {
@@ -499,7 +524,7 @@ __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdPara
     if (inside) {
         if (CHAIN) {
             ChainIO<MODE> io(p, (size_t)idx, sm, t);
-            gaussian_backward(p, g, idx, visible, acc, io);
+            gaussian_backward(p, idx, visible, gin, io);
             RawGrads r;
             float mean[3] = {0.f, 0.f, 0.f};
             if (visible) {
@@ -528,7 +553,7 @@ __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdPara
             else *o = r.drot;
         } else {
             StagedIO<MODE> io(p, (size_t)idx, sm, t);
-            gaussian_backward(p, g, idx, visible, acc, io);
+            gaussian_backward(p, idx, visible, gin, io);
         }
     }
     __syncthreads();
@@ -571,6 +596,170 @@ __global__ void __launch_bounds__(PBT) preprocess_backward_staged_kernel(BwdPara
     if (p.dL_dcolor) block_store<kAccOther, ST_V3>(p.dL_dcolor + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
 }
 
+
+// ================================ several views in one pass (chain mode) ================================
+// A view-sharded step owes every raw parameter the SUM of its gradients over the rank's views.  Launched per view, this stage
+// re-reads the Gaussian's parameters and SH row and read-modify-writes all 64 output floats once per view that sees it; here a
+// thread owns one Gaussian for ALL the views of the launch: it walks the views whose radii say "visible", runs the same
+// per-Gaussian math + packing chain on each view's accumulator row, sums the 16 chained gradients in registers and the 48 SH
+// gradients in its shared-memory row, and the block writes every output element exactly once, coalesced.
+constexpr int MAX_VIEWS = 8;      // views per launch (kernel-parameter space: 8 x ~0.5 KB); longer lists run in groups
+struct ViewSet {
+    int n;
+    BwdParams p[MAX_VIEWS];
+    GeomState g[MAX_VIEWS];
+};
+struct ViewsSmem {
+    float sh_in[PBT * (ST_SH + 1)];    // SH coefficients of the block's Gaussians (loaded once, read by every view)
+    float sh_acc[PBT * (ST_SH + 1)];   // sum over the views of dL/dsh
+    float mean3d[PBT * ST_V3];
+    float scale[PBT * ST_V3];
+    float color[PBT * ST_V3];
+    float scalar[3 * PBT];
+    unsigned char vis[PBT];            // visible in at least one view of the launch
+};
+struct ViewsIO {
+    static constexpr bool kAccParams = false, kAccOther = false, kAnyM = false;     // (only read on the culled path, unused here)
+    const BwdParams& p; size_t i; ViewsSmem& sm; int t; int sh_row;
+    float g_scale[3], g_feat[GS2M_NUM_FEATURES], g_mean[3], g_opac;
+    float4 g_rot;
+    __device__ ViewsIO(const BwdParams& p_, size_t i_, ViewsSmem& sm_, int t_) : p(p_), i(i_), sm(sm_), t(t_), sh_row((3 * p_.M) | 1) {}
+    __device__ void mean2d(float4 v) { if (p.dL_dmeans2D) reinterpret_cast<float4*>(p.dL_dmeans2D)[i] = v; }     // per view
+    __device__ void conic(float4 v) { if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[i] = v; }
+    __device__ void opacity(float v) { g_opac = v; }
+    __device__ void color(int, float) {}
+    __device__ void feature(int k, float v) { g_feat[k] = v; }
+    __device__ void mean3d(int k, float v) { g_mean[k] = v; }
+    __device__ void cov(int, float) {}
+    __device__ void scale(int k, float v) { g_scale[k] = v; }
+    __device__ void rot(float4 v) { g_rot = v; }
+    __device__ float sh_in(int k) const { return sm.sh_in[t * sh_row + k]; }
+    __device__ void sh_out(int k, float v) { sm.sh_acc[t * sh_row + k] += v; }
+};
+
+template <bool ACC>
+__global__ void __maxnreg__(144) preprocess_backward_views_kernel(const __grid_constant__ ViewSet vs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ViewsSmem& sm = *reinterpret_cast<ViewsSmem*>(smem_raw);
+    const BwdParams& p0 = vs.p[0];
+    const int t = threadIdx.x;
+    const size_t row0 = (size_t)p0.row_begin + (size_t)blockIdx.x * PBT;
+    const int rows = (int)min((size_t)PBT, (size_t)p0.row_end - row0);
+    const int idx = (int)row0 + t;
+    const bool inside = t < rows;
+    const int sh_row = 3 * p0.M, sh_pad = sh_row | 1;
+    // which views see this Gaussian
+    uint32_t vmask = 0;
+    if (inside) {
+#pragma unroll
+        for (int v = 0; v < MAX_VIEWS; ++v)
+            if (v < vs.n && __ldg(vs.p[v].radii + idx) > 0) vmask |= 1u << v;
+    }
+    sm.vis[t] = vmask != 0;
+    for (int k = 0; k < sh_pad; ++k) sm.sh_acc[t * sh_pad + k] = 0.f;
+    __syncthreads();
+    // coalesced load of the SH rows of the Gaussians some view sees
+    if (p0.shs != nullptr) {
+        const float* __restrict__ src = p0.shs + row0 * sh_row;
+        const int n = rows * sh_row;
+        if ((sh_row & 3) == 0) {
+            for (int e4 = t; e4 < (n >> 2); e4 += PBT) {
+                const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
+                if (sm.vis[r]) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + e4);
+                    float* d = sm.sh_in + r * sh_pad + c;
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            }
+        } else {
+            for (int e = t; e < n; e += PBT) {
+                const int r = e / sh_row, c = e - r * sh_row;
+                if (sm.vis[r]) sm.sh_in[r * sh_pad + c] = __ldg(src + e);
+            }
+        }
+        __syncthreads();
+    }
+    RawGrads sum;
+    float mean[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { sum.dscaling[k] = 0.f; sum.dalbedo[k] = 0.f; }
+    sum.drot = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum.dopacity = sum.droughness = sum.dmetallic = 0.f;
+    // the camera-independent half of the packing stage, once per Gaussian
+    Derived d;
+    SigmoidSlopes slopes;
+    float pos[3];
+    if (vmask) {
+        const PackIn in0{p0.P, p0.means3D, p0.chain.scaling_raw, p0.chain.rotation_raw, p0.chain.opacity_raw, p0.chain.albedo_raw,
+                         p0.chain.roughness_raw, p0.chain.metallic_raw, p0.viewmatrix, p0.cam_pos, p0.chain.z_depth, p0.chain.blend_metallic};
+        derive_gaussian(in0, idx, d, pos);
+        slopes = sigmoid_slopes(in0, idx);
+    }
+#pragma unroll 1
+    for (int v = 0; v < vs.n; ++v) {
+        if (!((vmask >> v) & 1u)) continue;
+        const BwdParams& p = vs.p[v];
+        const GeomState& g = vs.g[v];
+        GaussianInputs gin;
+        load_gaussian_inputs(p, g, (size_t)idx, true, gin);
+        ViewsIO io(p, (size_t)idx, sm, t);
+        gaussian_backward(p, idx, true, gin, io);
+        const PackIn in{p.P, p.means3D, p.chain.scaling_raw, p.chain.rotation_raw, p.chain.opacity_raw, p.chain.albedo_raw,
+                        p.chain.roughness_raw, p.chain.metallic_raw, p.viewmatrix, p.cam_pos, p.chain.z_depth, p.chain.blend_metallic};
+        derive_view(in, pos, d);
+        const RawGrads r = pack_chain(in, d, slopes, io.g_scale, io.g_rot, io.g_opac, io.g_feat);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mean[k] += io.g_mean[k] + r.dp[k];
+            sum.dscaling[k] += r.dscaling[k];
+            sum.dalbedo[k] += r.dalbedo[k];
+        }
+        sum.drot.x += r.drot.x; sum.drot.y += r.drot.y; sum.drot.z += r.drot.z; sum.drot.w += r.drot.w;
+        sum.dopacity += r.dopacity; sum.droughness += r.droughness; sum.dmetallic += r.dmetallic;
+    }
+    if (inside) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            sm.mean3d[t * ST_V3 + k] = mean[k];
+            sm.scale[t * ST_V3 + k] = sum.dscaling[k];
+            sm.color[t * ST_V3 + k] = sum.dalbedo[k];
+        }
+        sm.scalar[t] = sum.dopacity; sm.scalar[PBT + t] = sum.droughness; sm.scalar[2 * PBT + t] = sum.dmetallic;
+        float4* o = reinterpret_cast<float4*>(p0.chain.d_rotation_raw) + idx;
+        if (ACC) { if (vmask) red_add_f4(o, sum.drot); }
+        else *o = sum.drot;
+    }
+    __syncthreads();
+    if (p0.dL_dsh && sh_row > 0) {
+        float* __restrict__ dst = p0.dL_dsh + row0 * sh_row;
+        const int n = rows * sh_row;
+        if ((sh_row & 3) == 0) {
+            for (int e4 = t; e4 < (n >> 2); e4 += PBT) {
+                const int r = (4 * e4) / sh_row, c = (4 * e4) - r * sh_row;
+                if (ACC && !sm.vis[r]) continue;
+                const float* q = sm.sh_acc + r * sh_pad + c;
+                const float4 v = make_float4(q[0], q[1], q[2], q[3]);
+                float4* d4 = reinterpret_cast<float4*>(dst) + e4;
+                if (ACC) red_add_f4(d4, v);
+                else *d4 = v;
+            }
+        } else {
+            for (int e = t; e < n; e += PBT) {
+                const int r = e / sh_row, c = e - r * sh_row;
+                if (ACC && !sm.vis[r]) continue;
+                const float v = sm.sh_acc[r * sh_pad + c];
+                dst[e] = ACC ? dst[e] + v : v;
+            }
+        }
+    }
+    block_store<ACC, ST_V3>(p0.chain.d_xyz + row0 * ST_V3, sm.mean3d, rows * ST_V3, sm.vis);
+    block_store<ACC, ST_V3>(p0.chain.d_scaling_raw + row0 * ST_V3, sm.scale, rows * ST_V3, sm.vis);
+    block_store<ACC, ST_V3>(p0.chain.d_albedo_raw + row0 * ST_V3, sm.color, rows * ST_V3, sm.vis);
+    block_store<ACC, 1>(p0.chain.d_opacity_raw + row0, sm.scalar, rows, sm.vis);
+    block_store<ACC, 1>(p0.chain.d_roughness_raw + row0, sm.scalar + PBT, rows, sm.vis);
+    block_store<ACC, 1>(p0.chain.d_metallic_raw + row0, sm.scalar + 2 * PBT, rows, sm.vis);
+}
+
 }  // namespace
 
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s) {
@@ -603,6 +792,31 @@ int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStrea
         else preprocess_backward_generic_kernel<0><<<blocks, 256, 0, s>>>(p, g);
     }
     GS2M_CUDA(cudaGetLastError());
+    return GS2M_OK;
+}
+
+int launch_preprocess_backward_views(const BwdParams* ps, const GeomState* gs, int n_views, bool accumulate, cudaStream_t s) {
+    const BwdParams& p0 = ps[0];
+    if (p0.P == 0 || p0.row_end <= p0.row_begin || n_views <= 0) return GS2M_OK;
+    if (p0.M > 16 || !p0.has_chain) { set_error("backward_views needs a chain and M <= 16"); return GS2M_ERR_INVALID_ARGUMENT; }
+    static PerDeviceOnce configured;
+    int dev;
+    if (configured.need(dev)) {
+        GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_views_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViewsSmem)));
+        GS2M_CUDA(cudaFuncSetAttribute(preprocess_backward_views_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViewsSmem)));
+        configured.done(dev);
+    }
+    const int blocks = (p0.row_end - p0.row_begin + PBT - 1) / PBT;
+    for (int v0 = 0; v0 < n_views; v0 += MAX_VIEWS) {       // groups of MAX_VIEWS: the first overwrites (unless told to add)
+        ViewSet vs;
+        vs.n = std::min(MAX_VIEWS, n_views - v0);
+        for (int v = 0; v < vs.n; ++v) { vs.p[v] = ps[v0 + v]; vs.g[v] = gs[v0 + v]; }
+        for (int v = vs.n; v < MAX_VIEWS; ++v) { vs.p[v] = ps[v0]; vs.g[v] = gs[v0]; }
+        count_launches(1);
+        if (accumulate || v0 > 0) preprocess_backward_views_kernel<true><<<blocks, PBT, sizeof(ViewsSmem), s>>>(vs);
+        else preprocess_backward_views_kernel<false><<<blocks, PBT, sizeof(ViewsSmem), s>>>(vs);
+        GS2M_CUDA(cudaGetLastError());
+    }
     return GS2M_OK;
 }
 

@@ -234,6 +234,42 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
     roughness, metallic}, "z_depth": bool, "blend_metallic": bool}``: chain the gradients w.r.t. the activated scale / rotation /
     opacity, the features and the 3-D mean through GS-2M's packing stage of this view's camera inside the kernel and add them to the
     raw-parameter gradients in ``grads`` (``accumulate`` 0: overwritten, 2: ``+=``); ``grads["dL_dscale"]`` etc. may then be None."""
+    b, keep, grads = _backward_args(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features,
+                                    radii, raster_settings, state, grads, accumulate, densify_stats, phase, rows, chain)
+    if b is not None:
+        with torch.cuda.device(means3D.device):
+            _native.check(_native.load().gs2m_rasterize_backward(b), "gs2m_rasterize_backward")
+    return grads
+
+
+def backward_views_raw(views, rows=None, accumulate=False):
+    """The per-Gaussian stage (``phase="gaussians"``) of several views in ONE pass over the Gaussians ``rows`` (C-ABI
+    ``gs2m_rasterize_backward_views``).  ``views`` is a list of dicts holding, per view, the arguments of :func:`backward_raw`
+    (``grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features, radii, raster_settings,
+    state`` and optionally ``grads``, ``densify_stats``) and the same ``chain`` for all of them.  ``dL_dsh`` and the seven
+    raw-parameter gradients of the chain receive the SUM over the views, each element written once (``accumulate``: added to
+    what is there) — where a loop of per-view calls read-modify-writes them once per view."""
+    if not views:
+        return
+    built, keep_all = [], []
+    for k, v in enumerate(views):
+        b, keep, _ = _backward_args(v["grad_color"], v["grad_buffer"], v["means3D"], v["shs"], v.get("colors_precomp"), v["scales"],
+                                    v["rotations"], v.get("cov3D_precomp"), v["features"], v["radii"], v["raster_settings"],
+                                    v["state"], v.get("grads"), 2 if (accumulate or k > 0) else 0, v.get("densify_stats"),
+                                    "gaussians", rows, v["chain"])
+        if b is None:
+            return
+        built.append(b)
+        keep_all.append(keep)
+    arr = (_native.BackwardArgs * len(built))(*built)
+    with torch.cuda.device(views[0]["means3D"].device):
+        _native.check(_native.load().gs2m_rasterize_backward_views(arr, len(built)), "gs2m_rasterize_backward_views")
+
+
+def _backward_args(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, features,
+                   radii, raster_settings, state, grads, accumulate, densify_stats, phase, rows, chain):
+    """Validates one backward call and fills its C argument block.  Returns ``(block or None when P == 0, objects the block
+    points into, grads)``."""
     lib = _native.load()
     dev = means3D.device
     rs = raster_settings
@@ -274,7 +310,7 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
         if t is None or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous() or t.numel() != P * c:
             raise RuntimeError("grads[%r] must be a contiguous float32 tensor with %d x %d elements on %s" % (name, P, c, dev))
     if P == 0:
-        return grads
+        return None, None, grads
     with torch.cuda.device(dev):
         b = _native.BackwardArgs()
         b.P, b.D, b.M, b.R, b.R_capacity = P, int(rs.sh_degree), M, int(state.num_rendered), int(state.capacity)
@@ -322,8 +358,9 @@ def backward_raw(grad_color, grad_buffer, means3D, shs, colors_precomp, scales, 
                 if t is not None and (t.dtype != torch.float32 or t.numel() != P or not t.is_contiguous() or t.device != dev):
                     raise RuntimeError("densify_stats tensors must be contiguous float32 with P elements on the inputs' device")
             b.densify_grad_accum, b.densify_grad_accum_abs, b.densify_denom = (_ptr(t) for t in densify_stats)
-        _native.check(lib.gs2m_rasterize_backward(b), "gs2m_rasterize_backward")
-    return grads
+    keep = (means3D, shs_t, col_t, sca_t, rot_t, cov_t, fea_t, bg, vm, pm, cam, grad_color, grad_buffer, grads, radii, state,
+            chain, densify_stats, c if chain is not None else None)
+    return b, keep, grads
 
 
 def update_view_stats(radii, observe, max_radii2D=None, observe_cnt=None):

@@ -89,6 +89,7 @@ EXPORTS = [
     ("gs2m_last_error", C.c_char_p, []),
     ("gs2m_rasterize_forward", C.c_int, [C.POINTER(ForwardArgs)]),
     ("gs2m_rasterize_backward", C.c_int, [C.POINTER(BackwardArgs)]),
+    ("gs2m_rasterize_backward_views", C.c_int, [C.POINTER(BackwardArgs), C.c_int]),
     ("gs2m_last_instance_count", C.c_longlong, []),
     ("gs2m_geometry_bytes", C.c_size_t, [C.c_int]),
     ("gs2m_image_bytes", C.c_size_t, [C.c_int, C.c_int]),

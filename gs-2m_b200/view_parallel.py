@@ -347,16 +347,21 @@ class ViewShardedStep:
     def __init__(self, P: int, M: int, device, render_view: Optional[Callable[[int, GradientBuckets, bool], Optional[dict]]] = None,
                  world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1, buckets_cls=None,
                  begin_view: Optional[Callable[[int], dict]] = None,
-                 finish_view: Optional[Callable[[dict, object, bool, tuple], None]] = None, n_chunks: int = 4, buckets=None):
+                 finish_view: Optional[Callable[[dict, object, bool, tuple], None]] = None, n_chunks: int = 4, buckets=None,
+                 finish_views: Optional[Callable[[list, object, tuple], None]] = None):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
         self.device = torch.device(device)
         use_streams = n_streams > 1 and self.device.type == "cuda"
         self.n_streams = n_streams if use_streams else 1
         self.deferred = begin_view is not None
-        if self.deferred == (render_view is not None) or (self.deferred and finish_view is None):
-            raise ValueError("give either render_view, or begin_view together with finish_view")
+        if self.deferred == (render_view is not None) or (self.deferred and finish_view is None and finish_views is None):
+            raise ValueError("give either render_view, or begin_view together with finish_view / finish_views")
         self.begin_view, self.finish_view, self.P = begin_view, finish_view, P
+        # finish_views(handles, buckets, (begin, end)): the per-Gaussian stage of ALL the rank's views for one Gaussian range
+        # in one call (``backward_views_raw``: every output element written once with the sum over the views) — preferred
+        # over the per-view ``finish_view`` loop when given
+        self.finish_views = finish_views
         self.chunks = _row_chunks(P, n_chunks)
         buckets_cls = buckets_cls or GradientBuckets        # ParameterBuckets: raw-parameter gradients, chained per view
         # the deferred step sums all of a rank's views in ONE bucket set (its per-Gaussian stage runs on one stream)
@@ -406,8 +411,11 @@ class ViewShardedStep:
         for (b, e) in self.chunks:
             if not handles:
                 self.buckets.zero_rows(b, e)                      # more ranks than views: contribute zeros
-            for k, h in enumerate(handles):
-                self.finish_view(h, self.buckets, k > 0, (b, e))
+            if handles and self.finish_views is not None:
+                self.finish_views(handles, self.buckets, (b, e))
+            else:
+                for k, h in enumerate(handles):
+                    self.finish_view(h, self.buckets, k > 0, (b, e))
             if reduce:
                 works += self.buckets.all_reduce_rows(b, e, async_op=True)
                 works += self.stats.all_reduce_rows(b, e, async_op=True)

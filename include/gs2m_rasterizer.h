@@ -182,6 +182,18 @@ typedef struct gs2m_backward_args {
 
 int gs2m_rasterize_backward(const gs2m_backward_args* args);
 
+/* The per-Gaussian stage (phase 2) of `n_views` backward calls in ONE pass over the Gaussians — an extension for view-sharded
+ * callers; the reference has no counterpart (its backward is per view, rasterizer_impl.cu:334-438, and autograd sums the views).
+ * `views` is an array of n_views argument blocks, each exactly what gs2m_rasterize_backward would take for that view with
+ * phase = 2 and a chain: they must share P / D / M, means3D, shs, dL_dsh, the row range, the stream and the chain block (same raw
+ * parameters and the same seven raw-gradient outputs), and use SH colours and scale + rotation inputs.  Every thread owns one
+ * Gaussian, walks the views that see it and sums their raw-parameter gradients on chip, so each element of dL_dsh and of the
+ * seven chain outputs is written once with the sum over the views (views[0].accumulate = 0: overwritten, zeros for Gaussians no
+ * view sees; 2: added to what is there) instead of being read-modify-written once per view.  The per-view optional outputs
+ * (dL_dmeans2D, dL_dconic, the densify_* statistics) behave as in the per-view call.  Result = calling gs2m_rasterize_backward
+ * for views[0] with that accumulate mode and for the others with accumulate = 2, up to fp32 summation order. */
+int gs2m_rasterize_backward_views(const gs2m_backward_args* views, int n_views);
+
 /* Arena sizes the resize callbacks will be asked for (the `required<T>()` of rasterizer_impl.h:25-30). */
 size_t gs2m_geometry_bytes(int P);
 size_t gs2m_image_bytes(int width, int height);

@@ -11,12 +11,14 @@ import view_parallel as vp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_streams,deferred", [(1, False), (2, False), (1, True), (2, True), (1, "fused"), (2, "fused")])
-def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
-    """deferred = "fused": the packing chain runs inside the rasterizer's per-Gaussian backward (gs2m_backward_args::chain)."""
+@pytest.mark.parametrize("n_streams,deferred,n_views", [(1, False, 4), (2, False, 4), (1, True, 4), (2, True, 4), (1, "fused", 4),
+                                                        (2, "fused", 4), (1, "views", 4), (2, "views", 3), (2, "views", 11)])
+def test_parameter_step_matches_autograd_over_views(n_streams, deferred, n_views):
+    """deferred = "fused": the packing chain runs inside the rasterizer's per-Gaussian backward (gs2m_backward_args::chain);
+    "views": one multi-view pass per Gaussian range (gs2m_rasterize_backward_views; 11 views = two launches, the second adding)."""
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization.packing import activate_and_pack
-    P, W, H, F, M, n_views = 30_000, 320, 240, 10, 16, 4
+    P, W, H, F, M = 30_000, 320, 240, 10, 16
     scene = syn.scene_to(syn.make_scene(P, shell_fraction=0.6), "cuda")
     cams = [syn.camera_to(c, "cuda") for c in syn.make_cameras(n_views, W, H)]
     settings = [syn.raster_settings_for(c, F, dgr.GaussianRasterizationSettings) for c in cams]
@@ -57,7 +59,7 @@ def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
             s, q, o, f = activate_and_pack(*[raw[k] for k in order], cam.world_view_transform, cam.camera_center,
                                            blend_metallic=True)
         color, radii, observe, buffer, state = dgr.forward_raw(raw["xyz"], scene.shs, None, o, s, q, None, f, st)
-        h = dict(v=v, s=s, q=q, f=f, radii=radii, observe=observe, state=state)
+        h = dict(v=v, s=s, q=q, f=f, radii=radii, observe=observe, state=state, st=st)
         dgr.backward_raw(gc, gb, raw["xyz"], scene.shs, None, s, q, None, f, radii, st, state, grads=step.buckets.raster,
                          phase="blend")
         return h
@@ -73,11 +75,19 @@ def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
                          grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows)
         buckets.chain_rows(raw, cam.world_view_transform, cam.camera_center, h["radii"], rows[0], rows[1], blend_metallic=True)
 
+    def finish_views(handles, buckets, rows):
+        chain = buckets.chain_spec(raw, blend_metallic=True)
+        dgr.backward_views_raw([dict(grad_color=gc, grad_buffer=gb, means3D=raw["xyz"], shs=scene.shs, scales=h["s"], rotations=h["q"],
+                                     features=h["f"], radii=h["radii"], raster_settings=h["st"], state=h["state"],
+                                     grads=buckets.raster, densify_stats=step.stats.backward_args(), chain=chain)
+                                for h in handles], rows=rows)
+
     if deferred:
         step = vp.ViewShardedStep(P, M, "cuda", world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
-                                  begin_view=begin_view, finish_view=finish_view, n_chunks=5)
+                                  begin_view=begin_view, finish_view=finish_view, n_chunks=5,
+                                  finish_views=finish_views if deferred == "views" else None)
         assert len(step.chunks) == 5 and len(step.bucket_sets) == 1
-        step.buckets.fused_chain = deferred == "fused"
+        step.buckets.fused_chain = deferred in ("fused", "views")
     else:
         step = vp.ViewShardedStep(P, M, "cuda", render_view, world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets)
     for b in step.bucket_sets:
@@ -89,6 +99,16 @@ def test_parameter_step_matches_autograd_over_views(n_streams, deferred):
         err, l2 = helpers.grad_errors(got[k], expect[k])
         tol = 2e-3 if k in ("scaling", "rotation") else 1e-4      # the ill-conditioned conic backward feeds these two
         assert err <= tol and l2 <= tol, "%s: max %.3e l2 %.3e" % (k, err, l2)
+    if deferred == "views":      # the gradient-norm statistics of every view went through the same pass
+        vis_count = torch.zeros(P, device="cuda")
+        for v in range(n_views):
+            with torch.no_grad():
+                s, q, o, f = activate_and_pack(*[raw[k] for k in order], cams[v].world_view_transform, cams[v].camera_center,
+                                               blend_metallic=True)
+            _c, radii, _o, _b, _s = dgr.forward_raw(raw["xyz"], scene.shs, None, o, s, q, None, f, settings[v])
+            vis_count += (radii > 0).float()
+        assert torch.equal(step.stats.denom.view(-1), vis_count)
+        assert float(step.stats.xyz_gradient_accum.abs().max()) > 0.0
 
 
 def test_accumulate_mode_2_overwrites_the_view_dependent_tensors():
