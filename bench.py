@@ -14,6 +14,7 @@ through its own Python binding on the same workload (rank 0 only; the reference 
 build is absent it falls back to the CPU oracle port on a bounded sample.
 """
 import argparse
+import gc as pygc
 import json
 import os
 import subprocess
@@ -113,7 +114,7 @@ def run_ours(args, cfg, rank, world, device):
     P, W, H, F, M = cfg["P"], cfg["W"], cfg["H"], cfg["F"], 16
     V_per = args.views_per_rank
     n_views = world * V_per
-    my_views = list(vp.shard_views(n_views, world, rank))
+    my_views = list(vp.shard_views(n_views, world, rank))       # (re-assigned by cost below when N > 1)
     scene = syn.scene_to(syn.make_scene(P, shell_fraction=cfg["shell"], cluster=cfg.get("cluster"), opacity_cap=cfg.get("opacity_cap")), device)
     cams_cpu = syn.make_cameras(n_views, W, H, radius=cfg["cam_radius"])
     cams = {v: syn.camera_to(cams_cpu[v], device) for v in range(n_views)}       # all views: dp_check replays the whole batch
@@ -124,6 +125,28 @@ def run_ours(args, cfg, rank, world, device):
     blend_metallic = F in (2, 6, 10)
     stats = {}
     holder = {}
+
+    # ---- which rank renders which view (N > 1): a step waits for its slowest rank at every collective, and the views differ in
+    # cost (instance count: 6.9 .. 7.9 M on the ring of cameras), so the batch is dealt out by cost — each rank measures the
+    # instance counts of its contiguous share once (a training loop knows them from the camera's previous visit), the counts
+    # are all-gathered and every rank derives the same longest-first table.  Same batch, same views per rank, same sum.
+    assignment = None
+    if world > 1 and not args.contiguous_views:
+        mine_R = []
+        for v in my_views:
+            st = settings[v]
+            with torch.no_grad():
+                s_, q_, o_, f_ = activate_and_pack(*[raw[k] for k in order], st.viewmatrix, st.campos, blend_metallic=blend_metallic)
+            mine_R.append(float(dgr.forward_raw(raw["xyz"], scene.shs, None, o_, s_, q_, None, f_, st, for_backward=False)[4].num_rendered))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (my_views, mine_R))
+        costs = [0.0] * n_views
+        for vs_, rs_ in gathered:
+            for v, r_ in zip(vs_, rs_):
+                costs[v] = r_
+        assignment = vp.balance_views(costs, world)
+        my_views = assignment[rank]
+        stats["view_costs"] = costs
 
     # ---- the training-faithful chain: the features and the activated scale / rotation / opacity depend on the
     # camera, so every view runs  fused activation+packing forward -> rasterizer forward -> reverse blend  as soon as it is
@@ -160,7 +183,8 @@ def run_ours(args, cfg, rank, world, device):
     def make_step(begin, world_=world, rank_=rank, n_streams=args.streams, buckets=None):
         st_ = vp.ViewShardedStep(P, M, device, world=world_, rank=rank_, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
                                  begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets,
-                                 finish_views=None if args.per_view_finish else finish_views)
+                                 finish_views=None if args.per_view_finish else finish_views,
+                                 assignment=assignment if world_ == world else None)
         st_.buckets.fused_chain = True
         return st_
 
@@ -173,18 +197,23 @@ def run_ours(args, cfg, rank, world, device):
 
     def timed(step_, steps):
         holder["step"] = step_
-        barrier()
+        pygc.collect()      # a full collection of the interpreter's heap takes 0.1-0.3 s (torch alone is ~1 M objects); if the
+        pygc.freeze()       # cyclic GC chose to run one inside a timed region the launch queue would drain and the step times
+        barrier()           # would measure the host.  Collect now, park the survivors, keep the GC enabled.
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(steps):
+        for k in range(steps):
             step_.run(n_views)
+            marks[k].record()
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
         ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        stats["step_ms"] = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]    # this rank's steps, one by one
         return float(ms[0]), wall
 
     for _ in range(args.warmup):
@@ -194,11 +223,12 @@ def run_ours(args, cfg, rank, world, device):
     R = int(stats["R"])
 
     clocks = ClockSampler(device.index)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         clocks.start()
     # ---- timed region 1 (headline): device-resident inputs ----
     launches0 = lib.gs2m_launch_count()
     total_ms, _ = timed(step, args.steps)
+    headline_step_ms = list(stats["step_ms"])
     launches = torch.tensor([lib.gs2m_launch_count() - launches0], device=device, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(launches, op=dist.ReduceOp.SUM)
@@ -279,18 +309,22 @@ def run_ours(args, cfg, rank, world, device):
 
     def run_e2e(steps):
         holder["step"] = step_e2e
+        pygc.collect(); pygc.freeze()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(steps):
+        for k in range(steps):
             step_e2e.run(n_views)
+            marks[k].record()
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
         ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        stats["e2e_step_ms"] = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
         return float(ms[0]), wall
 
     run_e2e(1)
@@ -342,6 +376,31 @@ def run_ours(args, cfg, rank, world, device):
         if not dp_check["pass"] and rank == 0:
             print("dp_check FAILED: %s" % json.dumps(dp_check), file=sys.stderr)
 
+    # ---- where the N > 1 step time goes: the same step with the exchange switched off, slowest and fastest rank ----
+    comm = None
+    if world > 1:
+        holder["step"] = step
+        pygc.collect(); pygc.freeze()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step.run(n_views, reduce=False)
+        e1.record()
+        torch.cuda.synchronize(device)
+        own = torch.tensor([e0.elapsed_time(e1) / args.steps], device=device)
+        lo, hi = own.clone(), own.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        comm = {"ms_per_step_without_allreduce": {"slowest_rank": round(float(hi[0]), 3), "fastest_rank": round(float(lo[0]), 3)},
+                "views": "cost-balanced assignment (instance counts, longest first)" if assignment is not None else "contiguous split",
+                "what": "the headline step with the all-reduces left out, timed on every rank: the slowest rank bounds the "
+                        "step from below, the rest of ms_per_step is exposed exchange"}
+        if assignment is not None:
+            c = stats["view_costs"]
+            comm["instances_per_rank"] = [int(sum(c[v] for v in vs_)) for vs_ in assignment]
+        barrier()
+
     # ---- side leg: the rasterizer alone on given inputs (the reference arm's workload; round 1's headline): forward +
     # backward per view into the gradients of the rasterizer's own inputs (73 floats per Gaussian), same deferred step ----
     param_bytes = step.buckets.nbytes_reduced()
@@ -366,7 +425,7 @@ def run_ours(args, cfg, rank, world, device):
                          densify_stats=holder["step"].stats.backward_args())
 
     step_r = vp.ViewShardedStep(P, M, device, world=world, rank=rank, n_streams=args.streams, begin_view=begin_raster,
-                                finish_view=finish_raster, n_chunks=args.chunks)
+                                finish_view=finish_raster, n_chunks=args.chunks, assignment=assignment)
     holder["step"] = step_r
     for _ in range(2):
         step_r.run(n_views)
@@ -398,6 +457,7 @@ def run_ours(args, cfg, rank, world, device):
             iteration()
         torch.cuda.synchronize(device)
         n_it = max(2, args.steps * V_per // 4)
+        pygc.collect(); pygc.freeze()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -448,6 +508,8 @@ def run_ours(args, cfg, rank, world, device):
                    "l2_policy": "working set per view (%.1f GB algorithmic) exceeds the 126 MB L2; no flush needed"
                                 % (ab["total"] / 1e9)},
         "ms_per_view": round(per_view_ms, 4),
+        "step_ms": {"value": headline_step_ms, "e2e": stats.get("e2e_step_ms"),
+                    "what": "rank 0's timed steps one by one (CUDA events between the steps; the headline uses the bracket around all of them)"},
         "gpu_launches": int(launches[0]),
         "raster_only": {"value": round(raster_value, 3), "unit": UNIT, "ms_per_view": round(raster_view_ms, 4),
                         "allreduce_bytes": raster_bytes,
@@ -469,6 +531,7 @@ def run_ours(args, cfg, rank, world, device):
     }
     if dp_check is not None:
         line["dp_check"] = dp_check
+        line["scaling_breakdown"] = comm
     if dropin is not None:
         line["dropin"] = dropin
     if world == 1 and not args.no_cpu_baseline:
@@ -561,6 +624,7 @@ def run_reference(args, cfg, rank, world, device):
         step()
     torch.cuda.synchronize(device)
     clocks.start()
+    pygc.collect(); pygc.freeze()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -592,6 +656,10 @@ def main():
     ap.add_argument("--views-per-rank", type=int, default=8)
     ap.add_argument("--streams", type=int, default=2, help="views in flight per rank (CUDA streams)")
     ap.add_argument("--chunks", type=int, default=4, help="Gaussian ranges of the deferred per-Gaussian backward / all-reduce")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed regions")
+    ap.add_argument("--nccl-normal-priority", action="store_true", help="N > 1: NCCL on a normal-priority stream (default: high)")
+    ap.add_argument("--contiguous-views", action="store_true",
+                    help="N > 1: contiguous split of the batch over the ranks instead of the cost-balanced assignment")
     ap.add_argument("--per-view-finish", action="store_true",
                     help="run the per-Gaussian backward once per view (round-2a protocol) instead of one multi-view pass per range")
     ap.add_argument("--cpu-tiles", type=int, default=96, help="tiles of the bounded CPU-baseline sample")
@@ -613,7 +681,11 @@ def main():
     torch.cuda.set_device(device)
     if world > 1 and args.impl == "ours":
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL's kernels on a HIGH-priority stream: a finished Gaussian range's all-reduce and the next range's per-Gaussian
+        # kernel become runnable at the same moment, and the per-Gaussian kernel fills every SM's register file, so at equal
+        # priority the exchange's CTAs (hundreds of threads each) only get in when that grid drains, one range late
+        opts = None if args.nccl_normal_priority else dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
     try:
         line = run_ours(args, cfg, rank, world, device) if args.impl == "ours" else run_reference(args, cfg, rank, world, device)
         if line is not None:

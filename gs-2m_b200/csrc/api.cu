@@ -85,6 +85,9 @@ size_t BinState::carve(char* base, int R, BinState* out) {
     carve_array(p, b.vals_unsorted, n);
     carve_array(p, b.point_list, n);
     carve_array(p, b.masks, n);
+    carve_array(p, b.dense_gid, n * 8);
+    carve_array(p, b.dense_pos, n * 8);
+    carve_array(p, b.dense_block_totals, ((n + 511) / 512) * 8);
     carve_array(p, b.sort_temp, sort_temp_bytes(R));
     if (out) *out = b;
     return (size_t)(p - base) + 128;
@@ -99,6 +102,8 @@ size_t ImageState::carve(char* base, int W, int H, ImageState* out) {
     carve_array(p, im.n_contrib, n);
     carve_array(p, im.ranges, tiles);
     carve_array(p, im.tile_order, tiles);
+    carve_array(p, im.block_ranges, tiles * 8);
+    carve_array(p, im.n_contrib_dense, n);
     carve_array(p, im.bin_info, BIN_WORDS);
     if (out) *out = im;
     return (size_t)(p - base) + 128;
@@ -328,7 +333,7 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         if (rc != GS2M_OK) return rc;
         if ((in_input != 0) != (start == 1)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
         { StageTimer t(GS2M_STAGE_RANGES, s);
-          rc = launch_ranges_masks_keys(R_cap, r_used, p.tiles_x, p.tiles_y, tk[1], point_list, g, b.keys_sorted, im.ranges, b.masks, s); }
+          rc = launch_ranges_masks_keys(R_cap, r_used, p.tiles_x, p.tiles_y, tk[1], b, g, im, s); }
         if (rc != GS2M_OK) return rc;
     } else if (R_cap > 0) {
         const int key_bits = 32 + tile_bits((uint32_t)n_tiles);
@@ -345,17 +350,18 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
         if ((in_input != 0) != (start == 1)) { set_error("internal: sort buffer parity mismatch"); return GS2M_ERR_CUDA; }
         // tile ranges + footprint masks in one pass over the sorted list
         { StageTimer t(GS2M_STAGE_RANGES, s);
-          rc = launch_ranges_and_masks(R, p.tiles_x, p.tiles_y, b.keys_sorted, point_list, g, im.ranges, b.masks, s); }
+          rc = launch_ranges_and_masks(R, p.tiles_x, p.tiles_y, b, g, im, s); }
         if (rc != GS2M_OK) return rc;
     } else {
         StageTimer t(GS2M_STAGE_RANGES, s);
         rc = launch_identify_tile_ranges(0, b.keys_sorted, im.ranges, n_tiles, s);
         if (rc != GS2M_OK) return rc;
+        GS2M_CUDA(cudaMemsetAsync(im.block_ranges, 0, (size_t)n_tiles * 8 * sizeof(uint2), s));
     }
     { StageTimer t(GS2M_STAGE_RANGES, s); rc = launch_tile_order(n_tiles, im.ranges, im.tile_order, s); }
     if (rc != GS2M_OK) return rc;
     { StageTimer t(GS2M_STAGE_BLEND_FWD, s);
-      rc = launch_blend_forward(p, g, point_list, b.masks, im, a->out_color, a->out_observe, a->out_buffer, s); }
+      rc = launch_blend_forward(p, g, b, R_cap, im, a->out_color, a->out_observe, a->out_buffer, s); }
     if (rc != GS2M_OK) return rc;
     if (speculative && p.P > 0) {
         if (a->no_wait) return a->R_capacity;
@@ -370,7 +376,7 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
 long long gs2m_last_instance_count(void) { return g_last_R; }
 
 // Validates one backward call and assembles the kernels' view of it.  Returns GS2M_OK with `empty` set when there is nothing to do.
-struct BackwardCall { BwdParams p; GeomState g; BinState b; ImageState im; cudaStream_t s; bool empty; };
+struct BackwardCall { BwdParams p; GeomState g; BinState b; ImageState im; cudaStream_t s; bool empty; int R_carve; };
 
 static int assemble_backward(const gs2m_backward_args* a, BackwardCall& c) {
     c.empty = false;
@@ -440,6 +446,7 @@ static int assemble_backward(const gs2m_backward_args* a, BackwardCall& c) {
     p.has_chain = ch != nullptr;
     if (ch) p.chain = *ch; else memset(&p.chain, 0, sizeof(p.chain));
 
+    c.R_carve = R_carve;
     GeomState::carve(a->geometry_buffer, p.P, &c.g);
     BinState::carve(a->binning_buffer, R_carve, &c.b);
     ImageState::carve(a->image_buffer, p.W, p.H, &c.im);
@@ -461,7 +468,7 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     // forward state has to start from zero again.
     if (a->phase != 2) {
         if (a->grad_acc_dirty) GS2M_CUDA(cudaMemsetAsync(g.grad_acc, 0, (size_t)p.P * GS2M_ACC_STRIDE * sizeof(float), s));
-        { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, point_list, b.masks, im, s); }
+        { StageTimer t(GS2M_STAGE_BLEND_BWD, s); rc = launch_blend_backward(p, g, b, c.R_carve, im, s); }
         if (rc != GS2M_OK) return rc;
     }
     if (a->phase != 1 && p.row_end > p.row_begin) {
@@ -523,6 +530,8 @@ int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buff
         out->keys_sorted = b.keys_sorted;
         out->point_list = b.point_list;
         out->masks = b.masks;
+        out->dense_gid = b.dense_gid;
+        out->dense_pos = b.dense_pos;
     }
     if (image_buffer) {
         ImageState im;
@@ -531,6 +540,8 @@ int gs2m_state_view_get(int P, int width, int height, int R, char* geometry_buff
         out->n_contrib = im.n_contrib;
         out->ranges = reinterpret_cast<const uint32_t*>(im.ranges);
         out->bin_info = im.bin_info;
+        out->block_ranges = reinterpret_cast<const uint32_t*>(im.block_ranges);
+        out->n_contrib_dense = im.n_contrib_dense;
     }
     return GS2M_OK;
 }

@@ -157,10 +157,10 @@ static_assert(BLEND_WARPS % BWD_CTA_WARPS == 0, "CTA must hold a divisor of the 
 #endif
 template <int F>
 __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
-    const uint8_t* __restrict__ masks, int W, int H, int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
+    const uint2* __restrict__ block_ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ dense_gid,
+    int R_cap, int W, int H, int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, const float* __restrict__ final_T,
-    const uint32_t* __restrict__ n_contrib, const float* __restrict__ grad_color, const float* __restrict__ grad_buffer,
+    const uint32_t* __restrict__ n_contrib_dense, const float* __restrict__ grad_color, const float* __restrict__ grad_buffer,
     float* __restrict__ grad_acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NV = WarpSmemB<F>::NV;
@@ -178,12 +178,13 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     const size_t N = (size_t)W * H;
     const size_t pix = (size_t)py * W + px;
 
-    const uint2 range = ranges[tile];
-    const int n_list = (int)(range.y - range.x);
+    // this warp block's own list (footprint_masks.cu: the tile's entries whose mask has the block's bit, compacted)
+    const uint2 br = block_ranges[(size_t)tile * BLEND_WARPS + warp];
+    const int n_list = (int)(br.y - br.x);
 
     // per-pixel state
     const float T_final = inside ? final_T[pix] : 0.f;
-    const uint32_t my_contrib = inside ? n_contrib[pix] : 0u;
+    const uint32_t my_contrib = inside ? n_contrib_dense[pix] : 0u;      // last contributor + 1, in this list's coordinates
     float T = T_final;
     float dL[4 * NV];              // staged channel order: colour 0..2, 0, features 4..
 #pragma unroll
@@ -214,56 +215,33 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
     float S = 0.f, last_alpha = 0.f, last_cd = 0.f;
     int n_parked = 0, my_gid = 0;
 
-    // Software pipeline: list indices + footprint-mask bytes are fetched two steps ahead (registers), the records of the
-    // hits one step ahead (cp.async into the ring).  Lane l of step s looks at entry f = n_back-1-(32 s + l): back to front,
-    // lane 0 deepest.
-    const uint32_t* __restrict__ list = point_list + range.x;
-    const uint8_t* __restrict__ mlist = masks + range.x;
+    // Software pipeline: the list is walked back to front; reversed index r = 32 j + l (lane l, step j) is list entry
+    // n_back - 1 - r.  Lane l holds the Gaussian indices of its entries of steps j + 1 and j + 2 (coalesced loads two steps
+    // ahead); the records of a half-step (16 entries) are copied while the previous half-step is evaluated.
+    const uint32_t* __restrict__ list = dense_gid + (size_t)warp * R_cap + br.x;
     StagedRing<F>& ring = sm.ring;
-    auto fetch = [&](int step, int& g, uint32_t& m) {
-        const int f = n_back - 1 - (32 * step + lane);
-        g = (f >= 0) ? (int)list[f] : 0;
-        m = (f >= 0) ? mlist[f] : 0u;
-    };
-    int gq[LIST_AHEAD];            // gq[i], mq[i]: index and mask byte of this lane's entry in step (current + 1 + i)
-    uint32_t mq[LIST_AHEAD];
-    int tail = 0, h_cur;
+    const int half = lane >> 4;
+    auto fetch = [&](int step) { const int f = n_back - 1 - (32 * step + lane); return (f >= 0) ? (int)list[f] : 0; };
+    int g1 = fetch(1), g2 = fetch(2);
     {
-        int g0;
-        uint32_t m0;
-        fetch(0, g0, m0);
-#pragma unroll
-        for (int i = 0; i < LIST_AHEAD; ++i) fetch(1 + i, gq[i], mq[i]);
-        const bool hit = (m0 >> warp) & 1u;
-        const uint32_t word = __ballot_sync(0xffffffffu, hit);
-        h_cur = __popc(word);
-        stage_step<F>(ring, lane, hit, word, g0, n_back - 1 - lane, 0, rec_a, rec_b, rgb, features);
+        const int g0 = fetch(0);
+        stage_half<F>(ring, lane, half == 0 && lane < n_back, g0, rec_a, rec_b, rgb, features);
+        stage_half<F>(ring, lane, half == 1 && lane < n_back, g0, rec_a, rec_b, rgb, features);
     }
-
-    for (int base = 0; base < n_back; base += 32) {
-        // ---- issue the next step's records behind the current step's if the ring has room for both ----
-        const int f1 = n_back - 1 - (base + 32 + lane);
-        const int g1 = gq[0];
-        const bool hit1 = (mq[0] >> warp) & 1u;
-        const uint32_t word1 = __ballot_sync(0xffffffffu, hit1);
-        const int h1 = __popc(word1);
-        const bool fits = h_cur + h1 <= 32;
-        if (fits) {
-            stage_step<F>(ring, lane, hit1, word1, g1, f1, tail + h_cur, rec_a, rec_b, rgb, features);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+    const int n_half = (n_back + 15) >> 4;
+    for (int h = 0; h < n_half; ++h) {
+        cp_async_wait<1>();       // half-step h has landed (h + 1 may still be in flight)
         __syncwarp();
 
         // ---- evaluate (lane = pixel) / reduce (lane = parked entry) ----
         // Two list entries per iteration: their alpha evaluations (the long dependent chain with the expf) are
         // independent and written branch-free so the scheduler can interleave them; only the T / S recurrences and
         // the parking are sequential.
-        for (int k = 0; k < h_cur; k += 2) {
-            const int slot0 = (tail + k) & 31;
-            const bool two = k + 1 < h_cur;
-            const int slot1 = two ? ((tail + k + 1) & 31) : slot0;
+        const int r0 = h << 4, cnt = min(16, n_back - r0), s0 = (h & 1) << 4;
+        for (int k = 0; k < cnt; k += 2) {
+            const int slot0 = s0 + k;
+            const bool two = k + 1 < cnt;
+            const int slot1 = two ? slot0 + 1 : slot0;
             const float4 ra0 = ring.a[slot0], rb0 = ring.b[slot0];
             const float4 ra1 = ring.a[slot1], rb1 = ring.b[slot1];
             float G0, alpha0, G1, alpha1;
@@ -273,8 +251,9 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
                 v0 = pair_alpha_nb(ra0.x, ra0.y, ra0.z, ra0.w, rb0.x, rb0.y, pxf, pyf, dx, dy, G0, alpha0);
                 v1 = pair_alpha_nb(ra1.x, ra1.y, ra1.z, ra1.w, rb1.x, rb1.y, pxf, pyf, dx, dy, G1, alpha1);
             }
-            v0 = v0 && ((uint32_t)__float_as_int(rb0.w) < my_contrib);
-            v1 = v1 && two && ((uint32_t)__float_as_int(rb1.w) < my_contrib);
+            // a pixel blended exactly the entries in front of its last contributor
+            v0 = v0 && ((uint32_t)(n_back - 1 - (r0 + k)) < my_contrib);
+            v1 = v1 && two && ((uint32_t)(n_back - 2 - (r0 + k)) < my_contrib);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const bool v = u ? v1 : v0;
@@ -328,13 +307,14 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
                 }
             }
         }
-        __syncwarp();   // every lane is done reading this step's slots
-        tail = (tail + h_cur) & 31;
-        if (!fits) stage_step<F>(ring, lane, hit1, word1, g1, f1, tail, rec_a, rec_b, rgb, features);
-        h_cur = h1;
-#pragma unroll
-        for (int i = 0; i + 1 < LIST_AHEAD; ++i) { gq[i] = gq[i + 1]; mq[i] = mq[i + 1]; }
-        fetch(base / 32 + 1 + LIST_AHEAD, gq[LIST_AHEAD - 1], mq[LIST_AHEAD - 1]);
+        __syncwarp();   // every lane is done reading this half of the ring
+
+        // ---- refill it: half-step h + 2 = the entries of step (h >> 1) + 1 held by the lanes of half (h & 1) ----
+        stage_half<F>(ring, lane, half == (h & 1) && ((h + 2) << 4) + (lane & 15) < n_back, g1, rec_a, rec_b, rgb, features);
+        if (h & 1) {
+            g1 = g2;
+            g2 = fetch((h >> 1) + 3);
+        }
     }
     cp_async_wait<0>();   // no copy may still be in flight when the warp's shared memory is released
     if (n_parked > 0) {
@@ -344,8 +324,7 @@ __global__ void GS2M_BWD_BOUNDS blend_backward_kernel(
 }
 
 template <int F>
-int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
-             cudaStream_t s) {
+int launch_b(const BwdParams& p, const GeomState& g, const BinState& b, int R_cap, const ImageState& im, cudaStream_t s) {
     const unsigned grid = (unsigned)(p.tiles_x * p.tiles_y) * BWD_CTAS_PER_TILE;
     const size_t smem = sizeof(WarpSmemB<F>) * BWD_CTA_WARPS;
     static PerDeviceOnce configured;   // per kernel instantiation and per device; callers may use several host threads
@@ -358,9 +337,9 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
         configured.done(dev);
     }
     count_launches(1);
-    blend_backward_kernel<F><<<grid, BWD_CTA_WARPS * 32, smem, s>>>(im.ranges, im.tile_order, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
-                                                               g.conic_c_opac, g.rgb, p.features, p.background,
-                                                               im.final_T, im.n_contrib, p.grad_color, p.grad_buffer,
+    blend_backward_kernel<F><<<grid, BWD_CTA_WARPS * 32, smem, s>>>(im.block_ranges, im.tile_order, b.dense_gid, R_cap, p.W, p.H, p.tiles_x,
+                                                               g.xy_conic_ab, g.conic_c_opac, g.rgb, p.features, p.background,
+                                                               im.final_T, im.n_contrib_dense, p.grad_color, p.grad_buffer,
                                                                g.grad_acc);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
@@ -368,10 +347,9 @@ int launch_b(const BwdParams& p, const GeomState& g, const uint32_t* point_list,
 
 }  // namespace
 
-int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
-                          const ImageState& im, cudaStream_t s) {
+int launch_blend_backward(const BwdParams& p, const GeomState& g, const BinState& b, int R_cap, const ImageState& im, cudaStream_t s) {
     switch (p.F) {
-#define GS2M_CASE(N) case N: return launch_b<N>(p, g, point_list, masks, im, s);
+#define GS2M_CASE(N) case N: return launch_b<N>(p, g, b, R_cap, im, s);
         GS2M_CASE(0) GS2M_CASE(1) GS2M_CASE(2) GS2M_CASE(3) GS2M_CASE(4) GS2M_CASE(5)
         GS2M_CASE(6) GS2M_CASE(7) GS2M_CASE(8) GS2M_CASE(9) GS2M_CASE(10)
 #undef GS2M_CASE

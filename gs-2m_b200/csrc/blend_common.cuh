@@ -80,10 +80,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Staged records of the blend kernels: a 32-slot ring per warp that holds only the list entries whose footprint mask has
-// the warp's bit set ("hits"), compacted in list order.  Slot layout:
+// Staged records of the blend kernels.  A warp walks ITS list — the tile's entries whose footprint mask has the warp block's bit,
+// compacted once per view by footprint_masks.cu (dense_gid / block_ranges) — so every entry it loads is one it evaluates.
+// Entry e of the list is staged by lane e % 32 into slot e % 32 of a 32-slot ring, sixteen entries ("half-step") at a time:
+// while the warp evaluates one half of the ring the copies of the other half are in flight.  Slot layout:
 //   a   = (mean.x, mean.y, conic.a, conic.b)                    cp.async 16 B from the blend record
-//   b   = (conic.c, opacity | Gaussian index, list position)    cp.async 8 B + one 8-byte store by the owning lane
+//   b   = (conic.c, opacity | Gaussian index, -)                 cp.async 8 B + one store by the owning lane
 //   col = (r, g, b, 0) | f0..f3 | f4..f7 | f8, f9, -, -          cp.async 16 B (rgb) + 8 B per feature pair
 // Channel i of the blended vector therefore sits at position i for the colour and 4 + i for feature i; the '-' words are
 // never read as a used channel.
@@ -98,31 +100,22 @@ struct StagedRing {
 // position of blended channel ch (0..2 colour, 3.. features) inside the staged vector / the pair accumulators
 __host__ __device__ constexpr int staged_pos(int ch) { return ch < 3 ? ch : ch + 1; }
 
-// How many list steps of (index, mask byte) each lane keeps in flight in registers beyond the step being issued (measured on
-// config 4: 2 -> 1.028 / 1.796 ms forward / backward, 3 -> 1.063 / 1.800, 4 -> 1.068 / 1.805, 6 -> 1.048 / 1.881).
-#ifndef GS2M_LIST_AHEAD
-#define GS2M_LIST_AHEAD 2
-#endif
-constexpr int LIST_AHEAD = GS2M_LIST_AHEAD;
-
-// Issues the copies of one list step: lane l holds entry (gid, pos) of the step and `hit` says whether it is staged; `word`
-// is the ballot of `hit`; the hits go to slots slot_base, slot_base+1, ... (mod 32) in lane order.  Always commits one group
-// (possibly empty) so that every lane's group count stays in step.
+// Issues the copies of one half-step: the lanes with `active` stage their entry (Gaussian `gid`) into slot `lane`.  Always
+// commits one group (possibly empty) so that every lane's group count stays in step.
 template <int F>
-__device__ __forceinline__ void stage_step(StagedRing<F>& sm, int lane, bool hit, uint32_t word, int gid, int pos, int slot_base,
+__device__ __forceinline__ void stage_half(StagedRing<F>& sm, int lane, bool active, int gid,
                                            const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
                                            const float4* __restrict__ rgb, const float* __restrict__ features) {
-    if (hit) {
-        const int slot = (slot_base + __popc(word & ((1u << lane) - 1u))) & 31;
-        cp_async16(&sm.a[slot], rec_a + gid);
-        cp_async8(&sm.b[slot], rec_b + gid);
-        *reinterpret_cast<int2*>(&sm.b[slot].z) = make_int2(gid, pos);
-        cp_async16(&sm.col[0][slot], rgb + gid);
+    if (active) {
+        cp_async16(&sm.a[lane], rec_a + gid);
+        cp_async8(&sm.b[lane], rec_b + gid);
+        reinterpret_cast<int*>(&sm.b[lane])[2] = gid;
+        cp_async16(&sm.col[0][lane], rgb + gid);
         if (F > 0) {
             const float* frow = features + (size_t)gid * GS2M_NUM_FEATURES;
 #pragma unroll
             for (int i = 0; i < (F + 1) / 2; ++i)
-                cp_async8(reinterpret_cast<float2*>(&sm.col[1 + i / 2][slot]) + (i & 1), frow + 2 * i);
+                cp_async8(reinterpret_cast<float2*>(&sm.col[1 + i / 2][lane]) + (i & 1), frow + 2 * i);
         }
     }
     cp_async_commit();

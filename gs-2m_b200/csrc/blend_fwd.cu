@@ -31,11 +31,12 @@ static_assert(BLEND_WARPS % FWD_CTA_WARPS == 0, "CTA must hold a divisor of the 
 
 template <int F>
 __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_forward_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ point_list,
-    const uint8_t* __restrict__ masks, int W, int H, int tiles_x, const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
+    const uint2* __restrict__ block_ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ dense_gid,
+    const uint32_t* __restrict__ dense_pos, int R_cap, int W, int H, int tiles_x, const float4* __restrict__ rec_a,
+    const float4* __restrict__ rec_b, const float4* __restrict__ rgb,
     const float* __restrict__ features, const float* __restrict__ bg, float* __restrict__ final_T,
-    uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
-    float* __restrict__ out_buffer) {
+    uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_contrib_dense, float* __restrict__ out_color,
+    int* __restrict__ out_observe, float* __restrict__ out_buffer) {
     __shared__ StagedRing<F> sm_all[FWD_CTA_WARPS];
     constexpr int NV = StagedRing<F>::NV;
     constexpr int NP = StagedRing<F>::NPAIR;
@@ -50,12 +51,14 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_
     const bool inside = (px < W) && (py < H);
     const float pxf = (float)px, pyf = (float)py;
 
-    const uint2 range = ranges[tile];
-    const int n_list = (int)(range.y - range.x);
+    // this warp block's own list
+    const uint2 br = block_ranges[(size_t)tile * BLEND_WARPS + warp];
+    const int n_list = (int)(br.y - br.x);
+    const uint32_t* __restrict__ list = dense_gid + (size_t)warp * R_cap + br.x;
 
     bool done = !inside;
     float T = 1.0f;
-    uint32_t last_contributor = 0;
+    uint32_t last_contributor = 0;    // in the coordinates of this list
     // colour + feature accumulators as aligned pairs in the staged order (r,g) (b,-) (f0,f1) ...: one FMUL2 + one FFMA2 per
     // pair of channels, each half rounding exactly like the reference's scalar fma(T, alpha * c, C)
     float2 A[NP];
@@ -63,51 +66,29 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_
     for (int i = 0; i < NP; ++i) A[i] = make_float2(0.f, 0.f);
 
     bool warp_done = __all_sync(0xffffffffu, done);
-    // Software pipeline: list indices + footprint-mask bytes are fetched two steps ahead (registers), the records of the
-    // hits one step ahead (cp.async into the ring), so both latencies are covered by the blending of the current step.
-    const uint32_t* __restrict__ list = point_list + range.x;
-    const uint8_t* __restrict__ mlist = masks + range.x;
-    auto fetch = [&](int step, int& g, uint32_t& m) {
-        const int li = 32 * step + lane;
-        g = (li < n_list) ? (int)list[li] : 0;
-        m = (li < n_list) ? mlist[li] : 0u;
-    };
-    int gq[LIST_AHEAD];            // gq[i], mq[i]: index and mask byte of this lane's entry in step (current + 1 + i)
-    uint32_t mq[LIST_AHEAD];
-    int tail = 0, h_cur;
+    // Software pipeline: lane l holds the Gaussian index of entry 32 j + l for the steps j + 1 and j + 2 (registers, coalesced
+    // loads two steps ahead); the records of a half-step are copied while the previous half-step is being blended.
+    const int half = lane >> 4;
+    int g1 = (32 + lane < n_list) ? (int)list[32 + lane] : 0;
+    int g2 = (64 + lane < n_list) ? (int)list[64 + lane] : 0;
     {
-        int g0;
-        uint32_t m0;
-        fetch(0, g0, m0);
-#pragma unroll
-        for (int i = 0; i < LIST_AHEAD; ++i) fetch(1 + i, gq[i], mq[i]);
-        const bool hit = (m0 >> warp) & 1u;
-        const uint32_t word = __ballot_sync(0xffffffffu, hit);
-        h_cur = __popc(word);
-        stage_step<F>(sm, lane, hit, word, g0, lane, 0, rec_a, rec_b, rgb, features);
+        const int g0 = (lane < n_list) ? (int)list[lane] : 0;
+        stage_half<F>(sm, lane, half == 0 && lane < n_list, g0, rec_a, rec_b, rgb, features);
+        stage_half<F>(sm, lane, half == 1 && lane < n_list, g0, rec_a, rec_b, rgb, features);
     }
-    for (int base = 0; base < n_list && !warp_done; base += 32) {
-        // ---- issue the next step's records behind the current step's if the ring has room for both ----
-        const int g1 = gq[0];
-        const bool hit1 = (mq[0] >> warp) & 1u;
-        const uint32_t word1 = __ballot_sync(0xffffffffu, hit1);
-        const int h1 = __popc(word1);
-        const bool fits = h_cur + h1 <= 32;
-        if (fits) {
-            stage_step<F>(sm, lane, hit1, word1, g1, base + 32 + lane, tail + h_cur, rec_a, rec_b, rgb, features);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+    const int n_half = (n_list + 15) >> 4;
+    for (int h = 0; h < n_half && !warp_done; ++h) {
+        cp_async_wait<1>();       // half-step h has landed (h + 1 may still be in flight)
         __syncwarp();
 
-        // ---- blend the current step's hits in list order ----
+        // ---- blend the half-step's entries in list order ----
         // two entries per iteration: both alpha evaluations are independent and branch-free (interleaved by the
         // scheduler); the blend itself stays strictly in list order
-        for (int k = 0; k < h_cur && !warp_done; k += 2) {
-            const int slot0 = (tail + k) & 31;
-            const bool two = k + 1 < h_cur;
-            const int slot1 = two ? ((tail + k + 1) & 31) : slot0;
+        const int e0 = h << 4, cnt = min(16, n_list - e0), s0 = (h & 1) << 4;
+        for (int k = 0; k < cnt && !warp_done; k += 2) {
+            const int slot0 = s0 + k;
+            const bool two = k + 1 < cnt;
+            const int slot1 = two ? slot0 + 1 : slot0;
             const float4 ra0 = sm.a[slot0], rb0 = sm.b[slot0];
             const float4 ra1 = sm.a[slot1], rb1 = sm.b[slot1];
             float G0, alpha0, G1, alpha1;
@@ -137,7 +118,7 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_
                         }
                         obs = T > 0.5f;
                         T = test_T;
-                        last_contributor = (uint32_t)__float_as_int(u ? rb1.w : rb0.w) + 1u;
+                        last_contributor = (uint32_t)(e0 + k + u) + 1u;
                     }
                 }
                 const uint32_t ob = __ballot_sync(0xffffffffu, obs);
@@ -145,13 +126,15 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_
             }
             warp_done = __all_sync(0xffffffffu, done);
         }
-        __syncwarp();   // all lanes are done with this step's slots
-        tail = (tail + h_cur) & 31;
-        if (!fits) stage_step<F>(sm, lane, hit1, word1, g1, base + 32 + lane, tail, rec_a, rec_b, rgb, features);
-        h_cur = h1;
-#pragma unroll
-        for (int i = 0; i + 1 < LIST_AHEAD; ++i) { gq[i] = gq[i + 1]; mq[i] = mq[i + 1]; }
-        fetch(base / 32 + 1 + LIST_AHEAD, gq[LIST_AHEAD - 1], mq[LIST_AHEAD - 1]);
+        __syncwarp();   // all lanes are done with this half of the ring
+
+        // ---- refill it: half-step h + 2 = the entries of step (h >> 1) + 1 held by the lanes of half (h & 1) ----
+        stage_half<F>(sm, lane, half == (h & 1) && ((h + 2) << 4) + (lane & 15) < n_list, g1, rec_a, rec_b, rgb, features);
+        if (h & 1) {
+            g1 = g2;
+            const int e = (((h >> 1) + 3) << 5) + lane;
+            g2 = (e < n_list) ? (int)list[e] : 0;
+        }
     }
     cp_async_wait<0>();   // no copy may still be in flight when the warp's shared memory is released
 
@@ -159,7 +142,9 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_
         const size_t N = (size_t)W * H;
         const size_t pix = (size_t)py * W + px;
         final_T[pix] = T;
-        n_contrib[pix] = last_contributor;
+        // the reference's n_contrib counts positions in the TILE's list: one gather per pixel from the list's position column
+        n_contrib[pix] = last_contributor ? dense_pos[(size_t)warp * R_cap + br.x + last_contributor - 1u] + 1u : 0u;
+        n_contrib_dense[pix] = last_contributor;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) out_color[ch * N + pix] = __fmaf_rn(T, bg[ch], (ch & 1) ? A[ch >> 1].y : A[ch >> 1].x);
 #pragma unroll
@@ -171,23 +156,24 @@ __global__ void __launch_bounds__(FWD_CTA_WARPS * 32, 32 / FWD_CTA_WARPS) blend_
 }
 
 template <int F>
-int launch_f(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks, const ImageState& im,
+int launch_f(const FwdParams& p, const GeomState& g, const BinState& b, int R_cap, const ImageState& im,
              float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
     const unsigned grid = (unsigned)(p.tiles_x * p.tiles_y) * FWD_CTAS_PER_TILE;
     count_launches(1);
-    blend_forward_kernel<F><<<grid, FWD_CTA_WARPS * 32, 0, s>>>(im.ranges, im.tile_order, point_list, masks, p.W, p.H, p.tiles_x, g.xy_conic_ab,
-                                                           g.conic_c_opac, g.rgb, p.features, p.background, im.final_T,
-                                                           im.n_contrib, out_color, out_observe, out_buffer);
+    blend_forward_kernel<F><<<grid, FWD_CTA_WARPS * 32, 0, s>>>(im.block_ranges, im.tile_order, b.dense_gid, b.dense_pos, R_cap, p.W, p.H,
+                                                           p.tiles_x, g.xy_conic_ab, g.conic_c_opac, g.rgb, p.features, p.background,
+                                                           im.final_T, im.n_contrib, im.n_contrib_dense, out_color, out_observe,
+                                                           out_buffer);
     GS2M_CUDA(cudaGetLastError());
     return GS2M_OK;
 }
 
 }  // namespace
 
-int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
+int launch_blend_forward(const FwdParams& p, const GeomState& g, const BinState& b, int R_cap,
                          const ImageState& im, float* out_color, int* out_observe, float* out_buffer, cudaStream_t s) {
     switch (p.F) {
-#define GS2M_CASE(N) case N: return launch_f<N>(p, g, point_list, masks, im, out_color, out_observe, out_buffer, s);
+#define GS2M_CASE(N) case N: return launch_f<N>(p, g, b, R_cap, im, out_color, out_observe, out_buffer, s);
         GS2M_CASE(0) GS2M_CASE(1) GS2M_CASE(2) GS2M_CASE(3) GS2M_CASE(4) GS2M_CASE(5)
         GS2M_CASE(6) GS2M_CASE(7) GS2M_CASE(8) GS2M_CASE(9) GS2M_CASE(10)
 #undef GS2M_CASE

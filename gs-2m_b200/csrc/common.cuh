@@ -44,6 +44,9 @@ struct BinState {
     uint32_t* vals_unsorted;  // [R]
     uint32_t* point_list;     // [R]
     uint8_t*  masks;          // [R] footprint mask of every list entry (bit w: warp block w of the tile may be reached)
+    uint32_t* dense_gid;      // [8][R] per warp-block position w: the instance list compacted by mask bit w (Gaussian indices)
+    uint32_t* dense_pos;      // [8][R] ... and each entry's position inside its tile's list
+    uint32_t* dense_block_totals;   // [8][ceil(R/512)] scan scratch of the compaction
     char*     sort_temp;
     static size_t carve(char* base, int R, BinState* out);
 };
@@ -53,6 +56,8 @@ struct ImageState {
     uint32_t* n_contrib;      // [N]
     uint2*    ranges;         // [tiles]
     uint32_t* tile_order;     // [tiles] tile ids, longest lists first: the order in which the blend kernels' CTAs take the tiles
+    uint2*    block_ranges;   // [tiles][8] slice of dense_gid[w] that is the list of (tile, warp block w)
+    uint32_t* n_contrib_dense;   // [N] last contributor + 1 in the coordinates of the pixel's warp-block list (for the backward)
     uint32_t* bin_info;       // [8] control block written on the device: BIN_* indices below
     static size_t carve(char* base, int W, int H, ImageState* out);
 };
@@ -104,13 +109,11 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, ui
 int launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, int tiles_x, int tiles_y,
                                uint64_t* keys, uint32_t* vals, cudaStream_t s);
 int launch_identify_tile_ranges(int R, const uint64_t* keys_sorted, uint2* ranges, int n_tiles, cudaStream_t s);
-int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const uint64_t* keys_sorted, const uint32_t* point_list,
-                            const GeomState& g, uint2* ranges, uint8_t* masks, cudaStream_t s);
+int launch_ranges_and_masks(int R, int tiles_x, int tiles_y, const BinState& b, const GeomState& g, const ImageState& im, cudaStream_t s);
 // Count-dependent stages take a capacity (`*_cap`: sizes the grid) and a device pointer to the real count (`n_ptr`, may be
 // nullptr = the capacity is the count); the kernels process min(*n_ptr, cap) items.
 int launch_ranges_masks_keys(int R_cap, const uint32_t* n_ptr, int tiles_x, int tiles_y, const uint32_t* tile_keys_sorted,
-                             const uint32_t* point_list, const GeomState& g, uint64_t* keys64_out, uint2* ranges, uint8_t* masks,
-                             cudaStream_t s);
+                             const BinState& b, const GeomState& g, const ImageState& im, cudaStream_t s);
 // depth-first binning (binning_depthfirst.cu)
 size_t compact_temp_bytes(int n);
 int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals, uint32_t* bin_info, uint32_t R_capacity,
@@ -118,7 +121,7 @@ int binning_df_compact(int P, const GeomState& g, uint32_t* keys, uint32_t* vals
 int binning_df_emit(int V_cap, const uint32_t* n_ptr, const GeomState& g, const uint32_t* order, const int* radii, int tiles_x,
                     int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
 int launch_tile_order(int n_tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s);
-int launch_blend_forward(const FwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
+int launch_blend_forward(const FwdParams& p, const GeomState& g, const BinState& b, int R_cap,
                          const ImageState& im, float* out_color, int* out_observe, float* out_buffer, cudaStream_t s);
 
 struct BwdParams {
@@ -137,8 +140,7 @@ struct BwdParams {
     bool has_chain;                                                        // chain the gradients through the packing stage
     gs2m_param_chain chain;
 };
-int launch_blend_backward(const BwdParams& p, const GeomState& g, const uint32_t* point_list, const uint8_t* masks,
-                          const ImageState& im, cudaStream_t s);
+int launch_blend_backward(const BwdParams& p, const GeomState& g, const BinState& b, int R_cap, const ImageState& im, cudaStream_t s);
 int launch_preprocess_backward(const BwdParams& p, const GeomState& g, cudaStream_t s);
 // per-Gaussian stage of n views in one pass (chain mode): outputs written once with the sum over the views (`accumulate`: added)
 int launch_preprocess_backward_views(const BwdParams* ps, const GeomState* gs, int n_views, bool accumulate, cudaStream_t s);

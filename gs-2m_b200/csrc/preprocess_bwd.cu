@@ -24,6 +24,11 @@
 #define GS2M_PB_THREADS 64
 #endif
 
+// register cap of the staged kernel (64-thread blocks, 19 KB of shared memory: 11 blocks per SM need <= 93)
+#ifndef GS2M_PB_MAXNREG
+#define GS2M_PB_MAXNREG 88
+#endif
+
 namespace gs2m {
 namespace {
 
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_generic_kernel(BwdPar
 }
 
 template <int MODE, bool CHAIN>
-__global__ void __maxnreg__(88) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
+__global__ void __maxnreg__(GS2M_PB_MAXNREG) preprocess_backward_staged_kernel(BwdParams p, GeomState g) {
     constexpr bool kAccParams = AccPolicy<MODE>::kAccParams, kAccOther = AccPolicy<MODE>::kAccOther;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StageSmem& sm = *reinterpret_cast<StageSmem*>(smem_raw);

@@ -382,7 +382,8 @@ def update_view_stats(radii, observe, max_radii2D=None, observe_cnt=None):
 
 def state_view(P, raster_settings, state: RasterState):
     """Typed tensors aliasing the opaque arenas (tests only): depths, rec_a, rec_b, rgb, cov3D, clamped,
-    tiles_touched, point_offsets, grad_acc, keys_sorted, point_list, masks, final_T, n_contrib, ranges, bin_info."""
+    tiles_touched, point_offsets, grad_acc, keys_sorted, point_list, masks, dense_gid, dense_pos, final_T, n_contrib,
+    ranges, bin_info, block_ranges, n_contrib_dense."""
     lib = _native.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     R = int(state.num_rendered)
@@ -414,6 +415,11 @@ def state_view(P, raster_settings, state: RasterState):
     out["keys_sorted"] = view(bn, v.keys_sorted, R, torch.int64)
     out["point_list"] = view(bn, v.point_list, R, torch.int32)
     out["masks"] = view(bn, v.masks, R, torch.uint8)
+    cap = int(state.capacity) or R            # the per-warp-block lists are laid out [8][arena capacity]
+    out["dense_gid"] = view(bn, v.dense_gid, 8 * cap, torch.int32).view(8, cap)
+    out["dense_pos"] = view(bn, v.dense_pos, 8 * cap, torch.int32).view(8, cap)
+    out["block_ranges"] = view(im, v.block_ranges, 16 * tiles, torch.int32).view(tiles, 8, 2)
+    out["n_contrib_dense"] = view(im, v.n_contrib_dense, H * W, torch.int32).view(H, W)
     out["bin_info"] = view(im, v.bin_info, 8, torch.int32)
     out["final_T"] = view(im, v.final_T, H * W, torch.float32).view(H, W)
     out["n_contrib"] = view(im, v.n_contrib, H * W, torch.int32).view(H, W)

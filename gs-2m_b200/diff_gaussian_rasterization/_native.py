@@ -80,7 +80,8 @@ class AdamGroup(C.Structure):
 class StateView(C.Structure):
     _fields_ = [(n, _fp) for n in (
         "depths", "rec_a", "rec_b", "rgb", "cov3D", "clamped", "tiles_touched", "point_offsets", "grad_acc",
-        "keys_sorted", "point_list", "masks", "final_T", "n_contrib", "ranges", "bin_info")]
+        "keys_sorted", "point_list", "masks", "dense_gid", "dense_pos", "final_T", "n_contrib", "ranges", "bin_info",
+        "block_ranges", "n_contrib_dense")]
 
 
 # every symbol include/gs2m_rasterizer.h declares: (name, restype, argtypes)

@@ -42,6 +42,24 @@ def shard_views(n_views: int, world: int, rank: int) -> range:
     return range(start, start + base + (1 if rank < extra else 0))
 
 
+def balance_views(costs: List[float], world: int) -> List[List[int]]:
+    """Assignment of ``len(costs)`` views to ``world`` ranks with equal view counts (the first ``n % world`` ranks get one more,
+    like :func:`shard_views`) and nearly equal summed cost: longest-processing-time-first, ties and order resolved by view index
+    so every rank computes the same table from the same costs.  A view's cost is its instance count (tile-list entries), which a
+    training loop knows from the camera's previous visit; a step waits for its slowest rank at every collective, so the spread
+    of the ranks' sums is lost time."""
+    n = len(costs)
+    base, extra = divmod(n, world)
+    cap = [base + (1 if r < extra else 0) for r in range(world)]
+    load = [0.0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for v in sorted(range(n), key=lambda v: (-float(costs[v]), v)):
+        r = min((r for r in range(world) if len(out[r]) < cap[r]), key=lambda r: (load[r], r))
+        out[r].append(v)
+        load[r] += float(costs[v])
+    return [sorted(vs) for vs in out]
+
+
 def _dist_ready() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
@@ -348,7 +366,8 @@ class ViewShardedStep:
                  world: Optional[int] = None, rank: Optional[int] = None, n_streams: int = 1, buckets_cls=None,
                  begin_view: Optional[Callable[[int], dict]] = None,
                  finish_view: Optional[Callable[[dict, object, bool, tuple], None]] = None, n_chunks: int = 4, buckets=None,
-                 finish_views: Optional[Callable[[list, object, tuple], None]] = None):
+                 finish_views: Optional[Callable[[list, object, tuple], None]] = None,
+                 assignment: Optional[List[List[int]]] = None):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
         self.device = torch.device(device)
@@ -362,6 +381,8 @@ class ViewShardedStep:
         # in one call (``backward_views_raw``: every output element written once with the sum over the views) — preferred
         # over the per-view ``finish_view`` loop when given
         self.finish_views = finish_views
+        # optional table of view indices per rank (``balance_views``) replacing the contiguous split
+        self.assignment = assignment
         self.chunks = _row_chunks(P, n_chunks)
         buckets_cls = buckets_cls or GradientBuckets        # ParameterBuckets: raw-parameter gradients, chained per view
         # the deferred step sums all of a rank's views in ONE bucket set (its per-Gaussian stage runs on one stream)
@@ -374,6 +395,10 @@ class ViewShardedStep:
         self.stats = DensificationStats(P, device)
 
     def local_views(self, n_views: int) -> List[int]:
+        if self.assignment is not None:
+            if sorted(v for vs in self.assignment for v in vs) != list(range(n_views)) or len(self.assignment) != self.world:
+                raise ValueError("the assignment must place each of the %d views on exactly one of the %d ranks" % (n_views, self.world))
+            return list(self.assignment[self.rank])
         return list(shard_views(n_views, self.world, self.rank))
 
     def _one_view(self, v, buckets, accumulate):

@@ -219,11 +219,15 @@ typedef struct gs2m_state_view {
     const uint64_t* keys_sorted;    /* (tile << 32) | float_bits(depth) */
     const uint32_t* point_list;     /* sorted Gaussian indices */
     const uint8_t*  masks;          /* footprint mask of every list entry: bit w = warp block w of the tile may blend it */
+    const uint32_t* dense_gid;      /* [8,R] for each warp-block position w: point_list compacted (stably) by mask bit w */
+    const uint32_t* dense_pos;      /* [8,R] ... and each entry's position inside its tile's list */
     /* image arena */
     const float*    final_T;        /* [H*W] */
     const uint32_t* n_contrib;      /* [H*W] */
     const uint32_t* ranges;         /* [tiles,2] */
     const uint32_t* bin_info;       /* [8] {R, V, flags, R used by the kernels, V used, -, -, -}; flags: GS2M_BIN_* */
+    const uint32_t* block_ranges;   /* [tiles,8,2] the slice of dense_gid[w] that is the list of (tile, warp block w) */
+    const uint32_t* n_contrib_dense;/* [H*W] n_contrib in the coordinates of the pixel's warp-block list */
 } gs2m_state_view;
 enum { GS2M_BIN_OVERFLOW = 1, GS2M_BIN_PREFILTERED = 2, GS2M_BIN_TOO_LARGE = 4 };
 

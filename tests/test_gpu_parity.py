@@ -193,6 +193,37 @@ def test_sh_degrees_and_coefficient_counts(dgr, ref, deg, M):
         assert err <= grad_gate(k), "%s deg=%d M=%d err %.3e" % (k, deg, M, err)
 
 
+@pytest.mark.parametrize("path,P,W,H", [("depthfirst", 20_000, 321, 200), ("depthfirst-exact", 3_000, 97, 50), ("sort64", 20_000, 321, 200),
+                                        ("depthfirst", 150_000, 640, 361)])
+def test_warp_block_lists_are_the_stable_compaction_of_the_tile_lists(dgr, path, P, W, H, monkeypatch):
+    """footprint_masks.cu compacts the instance list once per warp-block position w by mask bit w (dense_gid / dense_pos /
+    block_ranges); the blend kernels walk those lists instead of filtering the tile's list.  Checked against the definition."""
+    monkeypatch.setenv("GS2M_BINNING", "sort64" if path == "sort64" else "depthfirst")
+    if path == "depthfirst-exact":
+        monkeypatch.setenv("GS2M_EXACT_BINNING", "1")
+    scene, cam, feats, gc, gb = helpers.make_view(P, W, H, 3, shell=0.7)
+    for _ in range(2):                       # second call: speculative capacity on the default path
+        o = helpers.run_ours(dgr, scene, cam, feats, 3)
+    R = o["R"]
+    lists, masks, ranges = o["point_list"][:R].cpu(), o["masks"][:R].cpu().to(torch.int32), o["ranges"].cpu()
+    tile_of = torch.repeat_interleave(torch.arange(ranges.shape[0]), (ranges[:, 1] - ranges[:, 0]).to(torch.int64))
+    assert tile_of.numel() == R
+    pos = torch.arange(R) - ranges[tile_of, 0].to(torch.int64)
+    br, dg, dp = o["block_ranges"].cpu().to(torch.int64), o["dense_gid"].cpu(), o["dense_pos"].cpu()
+    for w in range(8):
+        sel = ((masks >> w) & 1).bool()
+        n = int(sel.sum())
+        assert torch.equal(dg[w, :n], lists[sel]) and torch.equal(dp[w, :n].to(torch.int64), pos[sel]), w
+        counts = torch.zeros(ranges.shape[0], dtype=torch.int64).index_add_(0, tile_of[sel], torch.ones(n, dtype=torch.int64))
+        ends = torch.cumsum(counts, 0)
+        nonempty = ranges[:, 1] > ranges[:, 0]
+        assert torch.equal(br[nonempty, w, 1], ends[nonempty]) and torch.equal(br[nonempty, w, 0], (ends - counts)[nonempty]), w
+        assert int((br[~nonempty, w, 1] - br[~nonempty, w, 0]).abs().sum()) == 0
+    # the forward's last-contributor index in list coordinates maps back to the reference's through dense_pos
+    ncd, nc = o["n_contrib_dense"].cpu().to(torch.int64), o["n_contrib"].cpu().to(torch.int64)
+    assert torch.equal(ncd == 0, nc == 0)
+
+
 @pytest.mark.parametrize("path", ["depthfirst", "depthfirst-exact", "sort64"])
 def test_all_binning_paths_are_bit_exact(dgr, ref, path, monkeypatch):
     """GS2M_BINNING selects depth sort + emission in depth order + tile sort (default; speculative from the second call on,

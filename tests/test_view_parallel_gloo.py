@@ -134,3 +134,21 @@ def test_two_rank_step_equals_sequential_sum(tmp_path, n_views, param_buckets, d
         assert torch.equal(res[r]["denom"], denom)
         torch.testing.assert_close(res[r]["accum"], accum, rtol=1e-6, atol=1e-6)
         torch.testing.assert_close(res[r]["accum_abs"], accum_abs, rtol=1e-6, atol=1e-6)
+
+
+def test_balance_views_equal_counts_and_smaller_spread():
+    import random
+    rng = random.Random(3)
+    for world, n in ((8, 64), (4, 10), (3, 3), (5, 2)):
+        costs = [rng.uniform(6.5, 8.0) for _ in range(n)]
+        table = vp.balance_views(costs, world)
+        assert sorted(v for vs in table for v in vs) == list(range(n))
+        assert [len(vs) for vs in table] == [len(vp.shard_views(n, world, r)) for r in range(world)]
+        spread = lambda t: max(sum(costs[v] for v in vs) for vs in t) - min(sum(costs[v] for v in vs) for vs in t if vs or True)  # noqa: E731
+        contiguous = [list(vp.shard_views(n, world, r)) for r in range(world)]
+        assert spread(table) <= spread(contiguous) + 1e-9
+        assert vp.balance_views(costs, world) == table           # deterministic: every rank derives the same table
+    step = vp.ViewShardedStep(4, 1, "cpu", render_view=lambda v, b, a: None, world=2, rank=1, assignment=[[0, 3], [1, 2]])
+    assert step.local_views(4) == [1, 2]
+    with pytest.raises(ValueError):
+        vp.ViewShardedStep(4, 1, "cpu", render_view=lambda v, b, a: None, world=2, rank=0, assignment=[[0, 1], [1, 2]]).local_views(4)
