@@ -309,7 +309,6 @@ int gs2m_rasterize_forward(const gs2m_forward_args* a) {
     if (!bin_base) { set_error("binning_buffer callback returned NULL"); return GS2M_ERR_ALLOC; }
     BinState b;
     BinState::carve(bin_base, R_cap, &b);
-    const uint32_t* point_list = b.point_list;
     if (R_cap > 0 && path == BIN_DEPTHFIRST) {
         const uint32_t* v_used = im.bin_info + BIN_V_USED;
         const uint32_t* r_used = im.bin_info + BIN_R_USED;
@@ -462,7 +461,6 @@ int gs2m_rasterize_backward(const gs2m_backward_args* a) {
     const BinState& b = c.b;
     const ImageState& im = c.im;
     cudaStream_t s = c.s;
-    const uint32_t* point_list = b.point_list;
 
     // The accumulator rows of the visible Gaussians were zeroed by the forward (preprocess); a second backward over the same
     // forward state has to start from zero again.

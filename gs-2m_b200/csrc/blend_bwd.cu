@@ -5,14 +5,16 @@
 // float atomics per (pixel, Gaussian) pair.  This kernel produces the same sums (to fp32 re-association) with
 // *no per-pixel atomics* and *no block-wide barriers*:
 //
-//   warp-autonomous walk      A tile is 8 warps, each owning an 8x4 pixel block and walking the tile's list on its own,
-//                             32 entries per step (the CTA is only a scheduling unit: two warps per CTA, 96 registers,
-//                             20 warps per SM).  The footprint masks written by the forward say which entries reach the
-//                             warp's block; the ballot of the warp's bit is its work list and only the hit lanes gather
-//                             the 32-byte blend record and stage colour + features in shared memory.  Entries behind
-//                             the warp's deepest last-contributor are never touched.  (The round-1 first cut staged
-//                             batches per CTA behind __syncthreads; ncu showed 32% of the stall samples on those
-//                             barriers because the 8 warps of a tile have very unequal work.)
+//   warp-autonomous walk      A tile is 8 warps, each owning an 8x4 pixel block and walking its own list back to front
+//                             (the CTA is only a scheduling unit: two warps per CTA, 96 registers, 20 warps per SM).  The
+//                             list is the one the forward walked: the tile's entries whose footprint mask has the block's
+//                             bit, compacted by footprint_masks.cu (dense_gid / block_ranges), so every entry loaded is
+//                             evaluated.  Records, colour and features of sixteen entries at a time are copied global ->
+//                             shared with cp.async into one half of a 32-slot ring while the other half is evaluated.
+//                             Entries behind the warp's deepest last-contributor (n_contrib_dense, written by the forward
+//                             in list coordinates) are never touched.  (The round-1 first cut staged batches per CTA
+//                             behind __syncthreads; ncu showed 32% of the stall samples on those barriers because the 8
+//                             warps of a tile have very unequal work.)
 //   evaluate (lane = pixel)   For a surviving entry every lane recomputes alpha bit-exactly like the forward, steps
 //                             T <- T/(1-alpha) (MUFU.RCP + one Newton step), and needs only two scalars per pair:
 //                             w = alpha*T  (weight of the colour/feature gradients) and  Q = G * dL/dalpha  (weight of

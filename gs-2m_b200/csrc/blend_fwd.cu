@@ -4,13 +4,13 @@
 // Behavioural reference: renderCUDA (cuda_rasterizer/forward.cu:246-372).  Per pixel the sequence of
 // (power, alpha, test_T, T) values, the termination point, `n_contrib` and the `observe` counts are bit-identical to
 // the reference; what differs is how the work is organised:
-//   * warp-autonomous walk: a tile is 8 warps, each owning an 8x4 pixel block and walking the tile list on its own,
-//     32 entries per step, with no block-wide barrier anywhere (the CTA is only a scheduling unit: one warp per CTA).
-//     Lane l reads the footprint-mask byte of entry l (footprint_masks.cu: which of the tile's eight warp blocks the
-//     Gaussian can reach with alpha >= 1/255, computed once per instance and shared with the backward); the ballot of
-//     the warp's bit is its work list, and only the hit lanes gather the 32-byte blend record (two 128-bit loads, an
-//     L1/L2 hit for the other warps of the tile) and stage colour + feature vector as 16-byte shared records, instead
-//     of the reference's per-pair global re-fetches.  Indices and masks are fetched two steps ahead, records one;
+//   * warp-autonomous walk: a tile is 8 warps, each owning an 8x4 pixel block, with no block-wide barrier anywhere (the
+//     CTA is only a scheduling unit: one warp per CTA).  A warp walks ITS OWN list: footprint_masks.cu decides once per
+//     (Gaussian, tile) instance which of the tile's eight warp blocks the Gaussian can reach with alpha >= 1/255 and compacts
+//     the tile lists by that bit (dense_gid / block_ranges; shared with the backward), so every entry a warp loads is one it
+//     evaluates.  The 32-byte blend record, colour and feature vector of an entry are copied global -> shared with cp.async
+//     (LDGSTS) sixteen entries at a time, one half of a 32-slot ring being filled while the other is blended; the Gaussian
+//     indices are read two 32-entry steps ahead.  No per-pair global re-fetches as in the reference;
 //   * two entries are evaluated per iteration with branch-free alpha code; the blend itself stays in list order;
 //   * a warp stops as soon as all of its 32 pixels have terminated (the reference only leaves when all 256 have);
 //   * `observe` increments are aggregated per warp (ballot + popc): one integer reduction per (entry, warp) — sums of
