@@ -171,20 +171,20 @@ def run_ours(args, cfg, rank, world, device):
                          densify_stats=holder["step"].stats.backward_args(),
                          chain=buckets.chain_spec(raw, blend_metallic=blend_metallic))
 
-    def finish_views(handles, buckets, rows):
+    def finish_views(handles, buckets, rows, accumulate=False):
         # all of the rank's views for one Gaussian range in ONE pass (gs2m_rasterize_backward_views): each thread owns a
         # Gaussian, sums the views that see it on chip and writes the 64 raw-gradient floats once
         chain = buckets.chain_spec(raw, blend_metallic=blend_metallic)
         dgr.backward_views_raw([dict(grad_color=gc, grad_buffer=gb, means3D=raw["xyz"], shs=scene.shs, scales=h["s"], rotations=h["q"],
                                      features=h["f"], radii=h["radii"], raster_settings=h["st"], state=h["state"],
                                      grads=buckets.raster, densify_stats=holder["step"].stats.backward_args(), chain=chain)
-                                for h in handles], rows=rows)
+                                for h in handles], rows=rows, accumulate=accumulate)
 
-    def make_step(begin, world_=world, rank_=rank, n_streams=args.streams, buckets=None):
+    def make_step(begin, world_=world, rank_=rank, n_streams=args.streams, buckets=None, in_flight=None):
         st_ = vp.ViewShardedStep(P, M, device, world=world_, rank=rank_, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
                                  begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets,
                                  finish_views=None if args.per_view_finish else finish_views,
-                                 assignment=assignment if world_ == world else None)
+                                 assignment=assignment if world_ == world else None, max_views_in_flight=in_flight)
         st_.buckets.fused_chain = True
         return st_
 
@@ -341,7 +341,9 @@ def run_ours(args, cfg, rank, world, device):
         step.run(n_views)
         torch.cuda.synchronize(device)
         got = {k: t.clone() for k, t in step.buckets.tensors.items()}
-        seq_step = holder["step"] = make_step(begin_view, world_=1, rank_=0, n_streams=1, buckets=step.buckets)
+        # (the whole batch on one rank: V_per views between their two phases at a time, like the ranks themselves — 64 views
+        # of a 6 M scene would otherwise hold 64 x 3.5 GB of arenas)
+        seq_step = holder["step"] = make_step(begin_view, world_=1, rank_=0, n_streams=1, buckets=step.buckets, in_flight=V_per)
         seq_step.run(n_views, reduce=False)
         torch.cuda.synchronize(device)
         seq = {k: t.clone() for k, t in step.buckets.tensors.items()}

@@ -367,7 +367,7 @@ class ViewShardedStep:
                  begin_view: Optional[Callable[[int], dict]] = None,
                  finish_view: Optional[Callable[[dict, object, bool, tuple], None]] = None, n_chunks: int = 4, buckets=None,
                  finish_views: Optional[Callable[[list, object, tuple], None]] = None,
-                 assignment: Optional[List[List[int]]] = None):
+                 assignment: Optional[List[List[int]]] = None, max_views_in_flight: Optional[int] = None):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
         self.device = torch.device(device)
@@ -383,6 +383,7 @@ class ViewShardedStep:
         self.finish_views = finish_views
         # optional table of view indices per rank (``balance_views``) replacing the contiguous split
         self.assignment = assignment
+        self.max_views_in_flight = max_views_in_flight      # deferred step: views between their two phases at any time
         self.chunks = _row_chunks(P, n_chunks)
         buckets_cls = buckets_cls or GradientBuckets        # ParameterBuckets: raw-parameter gradients, chained per view
         # the deferred step sums all of a rank's views in ONE bucket set (its per-Gaussian stage runs on one stream)
@@ -410,43 +411,57 @@ class ViewShardedStep:
 
     def _run_deferred(self, mine: List[int], reduce: bool) -> Dict[str, torch.Tensor]:
         """Phase A: every view's forward + reverse blend (``begin_view``), round-robin over the streams.  Phase B: the
-        per-Gaussian stage of every view (``finish_view(handle, buckets, accumulate, (begin, end))``), Gaussian range by
-        Gaussian range on the main stream; as soon as a range has received all of the rank's views its all-reduce is queued
-        (NCCL's own stream), so it runs under the next range's kernels and only the last range's exchange is exposed."""
+        per-Gaussian stage of every view (``finish_views(handles, buckets, (begin, end), accumulate)``, or the per-view
+        ``finish_view(handle, buckets, accumulate, (begin, end))``), Gaussian range by Gaussian range on the main stream; as
+        soon as a range has received all of the rank's views its all-reduce is queued (NCCL's own stream), so it runs under
+        the next range's kernels and only the last range's exchange is exposed.
+
+        A view between its two phases holds its three arenas (a few GB at several million Gaussians).  With
+        ``max_views_in_flight`` the rank's views go through both phases in groups of that many, the later groups adding
+        to the buckets; the exchange then follows the last group."""
         cuda = self.device.type == "cuda"
-        handles = []
-        if cuda and self.n_streams > 1 and mine:
-            main = torch.cuda.current_stream(self.device)
-            ready = torch.cuda.Event()
-            ready.record(main)
-            for k, v in enumerate(mine):
-                j = k % self.n_streams
-                with torch.cuda.stream(self.streams[j]):
-                    if k < self.n_streams:
-                        self.streams[j].wait_event(ready)
-                    handles.append(self._begin(v))
-            for j in range(min(self.n_streams, len(mine))):
-                main.wait_stream(self.streams[j])
-            for h in handles:                                     # allocated on a side stream, consumed on the main one
-                _record_stream(h, main)
-        else:
-            handles = [self._begin(v) for v in mine]
+        multi = cuda and self.n_streams > 1 and bool(mine)
+        cap = self.max_views_in_flight or len(mine) or 1
+        groups = [mine[i:i + cap] for i in range(0, len(mine), cap)] or [[]]
+        main = torch.cuda.current_stream(self.device) if multi else None
         self.buckets.begin_rows()
         works = []
-        for (b, e) in self.chunks:
-            if not handles:
-                self.buckets.zero_rows(b, e)                      # more ranks than views: contribute zeros
-            if handles and self.finish_views is not None:
-                self.finish_views(handles, self.buckets, (b, e))
+        for gi, group in enumerate(groups):
+            handles = []
+            if multi:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                for k, v in enumerate(group):
+                    j = k % self.n_streams
+                    with torch.cuda.stream(self.streams[j]):
+                        if k < self.n_streams:
+                            self.streams[j].wait_event(ready)
+                        handles.append(self._begin(v))
+                for j in range(min(self.n_streams, len(group))):
+                    main.wait_stream(self.streams[j])
+                for h in handles:                                 # allocated on a side stream, consumed on the main one
+                    _record_stream(h, main)
             else:
-                for k, h in enumerate(handles):
-                    self.finish_view(h, self.buckets, k > 0, (b, e))
-            if reduce:
-                works += self.buckets.all_reduce_rows(b, e, async_op=True)
-                works += self.stats.all_reduce_rows(b, e, async_op=True)
+                handles = [self._begin(v) for v in group]
+            last = gi == len(groups) - 1
+            for (b, e) in self.chunks:
+                if not handles and gi == 0:
+                    self.buckets.zero_rows(b, e)                  # more ranks than views: contribute zeros
+                if handles and self.finish_views is not None:
+                    if gi > 0:
+                        self.finish_views(handles, self.buckets, (b, e), True)
+                    else:
+                        self.finish_views(handles, self.buckets, (b, e))
+                else:
+                    for k, h in enumerate(handles):
+                        self.finish_view(h, self.buckets, k > 0 or gi > 0, (b, e))
+                if reduce and last:
+                    works += self.buckets.all_reduce_rows(b, e, async_op=True)
+                    works += self.stats.all_reduce_rows(b, e, async_op=True)
+            del handles
         for w in works:
             w.wait()                                              # stream-level wait: later work sees the reduced gradients
-        if cuda and self.n_streams > 1 and mine:
+        if multi:
             for j in range(min(self.n_streams, len(mine))):       # the side streams' next step must wait for this one
                 self.streams[j].wait_stream(main)
         self.buckets.views_accumulated = len(mine)

@@ -75,17 +75,18 @@ def test_parameter_step_matches_autograd_over_views(n_streams, deferred, n_views
                          grads=buckets.raster, accumulate=2 if accumulate else 0, phase="gaussians", rows=rows)
         buckets.chain_rows(raw, cam.world_view_transform, cam.camera_center, h["radii"], rows[0], rows[1], blend_metallic=True)
 
-    def finish_views(handles, buckets, rows):
+    def finish_views(handles, buckets, rows, accumulate=False):
         chain = buckets.chain_spec(raw, blend_metallic=True)
         dgr.backward_views_raw([dict(grad_color=gc, grad_buffer=gb, means3D=raw["xyz"], shs=scene.shs, scales=h["s"], rotations=h["q"],
                                      features=h["f"], radii=h["radii"], raster_settings=h["st"], state=h["state"],
                                      grads=buckets.raster, densify_stats=step.stats.backward_args(), chain=chain)
-                                for h in handles], rows=rows)
+                                for h in handles], rows=rows, accumulate=accumulate)
 
     if deferred:
         step = vp.ViewShardedStep(P, M, "cuda", world=1, rank=0, n_streams=n_streams, buckets_cls=vp.ParameterBuckets,
                                   begin_view=begin_view, finish_view=finish_view, n_chunks=5,
-                                  finish_views=finish_views if deferred == "views" else None)
+                                  finish_views=finish_views if deferred == "views" else None,
+                                  max_views_in_flight=4 if n_views == 11 else None)
         assert len(step.chunks) == 5 and len(step.bucket_sets) == 1
         step.buckets.fused_chain = deferred in ("fused", "views")
     else:

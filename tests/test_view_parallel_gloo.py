@@ -73,7 +73,8 @@ def _worker(rank, world, port, n_views, P, M, out_dir, param_buckets=False, defe
 
         cls = vp.ParameterBuckets if param_buckets else None
         if deferred:
-            step = vp.ViewShardedStep(P, M, "cpu", buckets_cls=cls, begin_view=begin_view, finish_view=finish_view, n_chunks=3)
+            step = vp.ViewShardedStep(P, M, "cpu", buckets_cls=cls, begin_view=begin_view, finish_view=finish_view, n_chunks=3,
+                                      max_views_in_flight=2 if deferred == "capped" else None)   # rank 0: groups of 2 + 1 views
             assert len(step.chunks) == 3 and step.chunks[0][0] == 0 and step.chunks[-1][1] == P
         else:
             step = vp.ViewShardedStep(P, M, "cpu", render_view, buckets_cls=cls)
@@ -100,7 +101,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("n_views,param_buckets,deferred", [(5, False, False), (1, False, False), (5, True, False),
-                                                            (5, False, True), (1, True, True), (5, True, True)])
+                                                            (5, False, True), (1, True, True), (5, True, True),
+                                                            (5, False, "capped"), (5, True, "capped")])
 def test_two_rank_step_equals_sequential_sum(tmp_path, n_views, param_buckets, deferred):
     world, P, M = 2, (1500 if deferred else 37), 4         # 1500 Gaussians: three 256-aligned, shrinking ranges in the deferred step
     mp.spawn(_worker, args=(world, _free_port(), n_views, P, M, str(tmp_path), param_buckets, deferred), nprocs=world, join=True)
