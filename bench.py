@@ -53,10 +53,16 @@ def algorithmic_bytes(P, V, R, N, F, M, tiles):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run.
+
+    The poller is started BEFORE the warm-up steps and only terminated when the whole run is over: starting or ending an
+    nvidia-smi process next to a running CUDA job stalls that job for tens of milliseconds (seen as a single 40-60 ms step, or a
+    whole leg at a third of its speed, in about one run out of eight when the poller was started right in front of the first
+    timed step and terminated right in front of another leg).  `summary()` uses the samples that fall inside the timed
+    windows (`window()` context manager)."""
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.windows = index, [], None, []
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -72,16 +78,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+            self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    class _Window:
+        def __init__(self, owner):
+            self.owner = owner
+
+        def __enter__(self):
+            self.t0 = time.perf_counter()
+
+        def __exit__(self, *exc):
+            self.owner.windows.append((self.t0, time.perf_counter()))
+
+    def window(self):
+        return ClockSampler._Window(self)
+
+    def summary(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
-        self.proc.terminate()
+        inside = [s for t, s in list(self.samples) if any(a - 0.2 <= t <= b + 0.2 for a, b in self.windows)]
+        use = inside or [s for _t, s in list(self.samples)]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in use:
             try:
                 sm.append(float(s[0])); mx.append(float(s[1]))
             except Exception:
@@ -92,6 +112,11 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.proc = None
 
 
 def build_workload(cfg, n_views_total, my_views, device):
@@ -216,18 +241,19 @@ def run_ours(args, cfg, rank, world, device):
         stats["step_ms"] = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]    # this rank's steps, one by one
         return float(ms[0]), wall
 
+    clocks = holder["clocks"] = ClockSampler(device.index)
+    if rank == 0 and not args.no_clock_sampler:
+        clocks.start()          # (before the warm-up, terminated at the very end of the run: see ClockSampler)
     for _ in range(args.warmup):
         step.run(n_views)
     barrier()
     V_vis = int((stats["radii"] > 0).sum())
     R = int(stats["R"])
 
-    clocks = ClockSampler(device.index)
-    if rank == 0 and not args.no_clock_sampler:
-        clocks.start()
     # ---- timed region 1 (headline): device-resident inputs ----
     launches0 = lib.gs2m_launch_count()
-    total_ms, _ = timed(step, args.steps)
+    with clocks.window():
+        total_ms, _ = timed(step, args.steps)
     headline_step_ms = list(stats["step_ms"])
     launches = torch.tensor([lib.gs2m_launch_count() - launches0], device=device, dtype=torch.int64)
     if world > 1:
@@ -328,9 +354,10 @@ def run_ours(args, cfg, rank, world, device):
         return float(ms[0]), wall
 
     run_e2e(1)
-    e2e_ms, wall_ms = run_e2e(args.steps)
+    with clocks.window():
+        e2e_ms, wall_ms = run_e2e(args.steps)
     e2e_value = n_views * args.steps / (e2e_ms * 1e-3)
-    clock_info = clocks.stop() if rank == 0 else None
+    clock_info = clocks.summary() if rank == 0 else None
 
     # ---- data-parallel correctness, outside the timed regions (N > 1): after one step every rank must hold the gradient of
     # the WHOLE batch, i.e. what a single rank gets by running all world*V views one after the other, and all ranks must
@@ -531,6 +558,7 @@ def run_ours(args, cfg, rank, world, device):
         "stage_ms_per_view": {k: round(v[0] / n_prof, 4) for k, v in stage.items()},
         "clocks": clock_info,
     }
+    clocks.stop()            # every GPU leg is over
     if dp_check is not None:
         line["dp_check"] = dp_check
         line["scaling_breakdown"] = comm
@@ -622,18 +650,21 @@ def run_reference(args, cfg, rank, world, device):
             torch.autograd.backward([color, buffer], [gc, gb])   # gradients accumulate in .grad across the views
 
     clocks = ClockSampler(device.index)
+    clocks.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(device)
-    clocks.start()
     pygc.collect(); pygc.freeze()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(device)
+    with clocks.window():
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(device)
     total_ms = e0.elapsed_time(e1)
+    clock_info = clocks.summary()
+    clocks.stop()
     value = V_per * args.steps / (total_ms * 1e-3)
     return {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
@@ -645,7 +676,7 @@ def run_reference(args, cfg, rank, world, device):
                              "sample": "compiled reference CUDA rasterizer (oracle/_ref, sm_100 build of the unmodified "
                                        "sources) on the GPU through its own Python binding; full workload, no sampling"},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "clocks": clocks.stop()}
+            "clocks": clock_info}
 
 
 def main():

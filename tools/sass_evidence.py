@@ -15,10 +15,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "gs-2m_b200", "lib", "libgs2m_rasterizer.so")
 DEFAULT = ["blend_forward_kernelILi10E", "blend_backward_kernelILi10E", "preprocess_forward_kernelILb1E",
-           "preprocess_backward_staged_kernelILi0E", "preprocess_backward_staged_kernelILi2E", "ranges_and_masks_kernelIjE",
-           "rs_onesweep_kernelIjE"]
+           "preprocess_backward_staged_kernelILi0E", "preprocess_backward_views_kernelILb0E", "ranges_and_masks_kernelIjE",
+           "dense_fill_kernel", "rs_onesweep_kernelIjE"]
 WATCH = ["REDG", "RED.", "ATOMG", "ATOMS", "MUFU.EX2", "MUFU.RCP", "MUFU.RSQ", "MUFU.LG2", "VOTE", "SHFL", "MATCH", "LDL", "STL",
-         "LDS", "STS", "LDG", "STG", "FFMA", "FMUL", "FADD", "BAR", "UTMALDG", "UTMASTG", "LDGSTS", "HMMA", "UTCHMMA", "REDUX"]
+         "LDS", "STS", "LDG", "STG", "FFMA2", "FMUL2", "FFMA", "FMUL", "FADD", "BAR", "UTMALDG", "UTMASTG", "LDGSTS", "HMMA", "UTCHMMA", "REDUX"]
 
 
 def sh(cmd):
@@ -57,8 +57,9 @@ def main():
                 n += 1
                 op = m.group(1)
                 full[op] += 1
+                base = op.split(".")[0]
                 for k in WATCH:
-                    if op.startswith(k):
+                    if (base == k) if k in ("FFMA", "FMUL", "FADD", "FFMA2", "FMUL2") else op.startswith(k):
                         ops[k] += 1
             out.append("## %s" % demangled)
             out.append("mangled: %s" % fn)
@@ -82,8 +83,8 @@ def main():
         f.write("# Registers / stack / static shared memory / local memory of every kernel (`cuobjdump -res-usage` of the built library)\n\n")
         spills = ", ".join("`%s` (%s B)" % (r[0], r[2]) for r in rows if r[2] not in ("0", None)) or "none"
         f.write("Kernels with a stack frame (register spills): " + spills + ".  Dynamic shared memory is not listed here: "
-                "`blend_backward_kernel<F>` takes sizeof(WarpSmemB<F>) x 2 warps (9.4 KB at F = 10), "
-                "`preprocess_backward_staged_kernel` 76 KB per 256-thread block.\n\n")
+                "`blend_backward_kernel<F>` takes sizeof(WarpSmemB<F>) x 2 warps (18.7 KB per CTA at F = 10), "
+                "`preprocess_backward_staged_kernel` 19 KB and `preprocess_backward_views_kernel` 28 KB per 64-thread block.\n\n")
         f.write("| kernel | registers | stack | static smem | local |\n|---|---|---|---|---|\n")
         for r in rows:
             f.write("| `%s` | %s | %s | %s | %s |\n" % r)
