@@ -380,6 +380,18 @@ def update_view_stats(radii, observe, max_radii2D=None, observe_cnt=None):
                       "gs2m_view_stats_update")
 
 
+def control_block(raster_settings, state: RasterState):
+    """The forward's device-side control block (int32[8]: R, V, flags, R used, V used, ...) as a tensor aliasing the image arena.
+    A caller that renders with ``no_wait=True`` never learns on the host whether the instance capacity sufficed; it can OR
+    ``control_block(...)[2]`` of its views into a device flag word and read that once per step (flag bits: ``GS2M_BIN_*``)."""
+    lib = _native.load()
+    H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+    v = _native.StateView()
+    _native.check(lib.gs2m_state_view_get(0, W, H, 0, None, None, _ptr(state.img), v), "gs2m_state_view_get")
+    off = v.bin_info - state.img.data_ptr()
+    return state.img[off:off + 32].view(torch.int32)
+
+
 def state_view(P, raster_settings, state: RasterState):
     """Typed tensors aliasing the opaque arenas (tests only): depths, rec_a, rec_b, rgb, cov3D, clamped,
     tiles_touched, point_offsets, grad_acc, keys_sorted, point_list, masks, dense_gid, dense_pos, final_T, n_contrib,

@@ -367,7 +367,8 @@ class ViewShardedStep:
                  begin_view: Optional[Callable[[int], dict]] = None,
                  finish_view: Optional[Callable[[dict, object, bool, tuple], None]] = None, n_chunks: int = 4, buckets=None,
                  finish_views: Optional[Callable[[list, object, tuple], None]] = None,
-                 assignment: Optional[List[List[int]]] = None, max_views_in_flight: Optional[int] = None):
+                 assignment: Optional[List[List[int]]] = None, max_views_in_flight: Optional[int] = None,
+                 max_steps_ahead: Optional[int] = None):
         self.world = world if world is not None else (dist.get_world_size() if _dist_ready() else 1)
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_ready() else 0)
         self.device = torch.device(device)
@@ -384,6 +385,8 @@ class ViewShardedStep:
         # optional table of view indices per rank (``balance_views``) replacing the contiguous split
         self.assignment = assignment
         self.max_views_in_flight = max_views_in_flight      # deferred step: views between their two phases at any time
+        self.max_steps_ahead = max_steps_ahead              # deferred step: steps the host may queue ahead of the running one
+        self._step_done: list = []
         self.chunks = _row_chunks(P, n_chunks)
         buckets_cls = buckets_cls or GradientBuckets        # ParameterBuckets: raw-parameter gradients, chained per view
         # the deferred step sums all of a rank's views in ONE bucket set (its per-Gaussian stage runs on one stream)
@@ -475,9 +478,20 @@ class ViewShardedStep:
 
     def run(self, n_views: int, reduce: bool = True) -> Dict[str, torch.Tensor]:
         mine = self.local_views(n_views)
+        if self.max_steps_ahead and self.device.type == "cuda":
+            # a host that never waits (no_wait forwards) may queue no more than `max_steps_ahead` steps behind the one the GPU
+            # is working on: every queued step holds its views' arenas, and a caching allocator that has to grow in the middle
+            # of a run (cudaMalloc synchronises the device) costs far more than the wait
+            while len(self._step_done) >= self.max_steps_ahead + 1:
+                self._step_done.pop(0).synchronize()
         self.stats.zero_()
         if self.deferred:
-            return self._run_deferred(mine, reduce)
+            out = self._run_deferred(mine, reduce)
+            if self.max_steps_ahead and self.device.type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._step_done.append(ev)
+            return out
         if not mine:  # more ranks than views: contribute zeros
             self.buckets.zero_()
         if self.n_streams == 1:
