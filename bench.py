@@ -177,19 +177,22 @@ def run_ours(args, cfg, rank, world, device):
     # camera, so every view runs  fused activation+packing forward -> rasterizer forward -> reverse blend  as soon as it is
     # scheduled, and the per-Gaussian backward + fused packing backward (+= into the nine RAW parameter-gradient groups, 64
     # floats per Gaussian) afterwards, Gaussian range by Gaussian range, each finished range all-reduced under the next one.
-    # Forward calls of the timed legs never wait for the device: the instance capacity of the binning arena is fixed after the
-    # warm-up (1.25 x the largest count seen + 64 Ki, the wrapper's own rule) and the forward is told not to read the count back
-    # (`no_wait`), so the host can queue a whole step ahead instead of waking up once per view — a host thread that is
-    # descheduled for a few milliseconds then no longer drains the GPU's queue.  Whether the capacity sufficed is a bit in each
-    # view's device-side control block; the bits are OR-ed into one word on the device and read once per timed region.
+    # Forward calls of the timed legs use ONE instance capacity for the binning arena, fixed after the warm-up (1.25 x the largest
+    # count seen + 64 Ki, the wrapper's own rule): the wrapper's automatic hint moves with every view, and an arena whose size is
+    # new to torch's caching allocator costs a cudaMalloc of ~1 GB in the middle of a step.  By default the forward still waits for
+    # its count (and raises if the capacity did not suffice).  With --no-wait-forward it does not (`no_wait`): the host queues a
+    # step ahead (bounded by max_steps_ahead), and whether the capacity sufficed is a bit in each view's device-side control
+    # block; the bits are OR-ed into one word on the device and read once per timed region.
     holder["cap"], holder["maxR"] = None, 0
     holder["ovf"] = torch.zeros(1, dtype=torch.int32, device=device)
 
     def forward(*a):
-        cap = None if args.waiting_forward else holder["cap"]
-        if cap:
+        cap = holder["cap"]
+        if cap and args.no_wait_forward:
             out = dgr.forward_raw(*a, capacity=cap, no_wait=True)
             holder["ovf"].bitwise_or_(dgr.control_block(a[-1], out[4])[2:3])
+        elif cap:
+            out = dgr.forward_raw(*a, capacity=cap)
         else:
             out = dgr.forward_raw(*a)
             holder["maxR"] = max(holder["maxR"], int(out[4].num_rendered))
@@ -234,7 +237,7 @@ def run_ours(args, cfg, rank, world, device):
                                  begin_view=begin, finish_view=finish_view, n_chunks=args.chunks, buckets=buckets,
                                  finish_views=None if args.per_view_finish else finish_views,
                                  assignment=assignment if world_ == world else None, max_views_in_flight=in_flight,
-                                 max_steps_ahead=None if args.waiting_forward else 1)
+                                 max_steps_ahead=1 if args.no_wait_forward else None)
         st_.buckets.fused_chain = True
         return st_
 
@@ -274,9 +277,9 @@ def run_ours(args, cfg, rank, world, device):
     barrier()
     V_vis = int((stats["radii"] > 0).sum())
     R = int(stats["R"])
-    holder["cap"] = int(holder["maxR"] * 1.25) + 65536          # the timed legs run without waiting from here on
-    for _ in range(3):                                          # (warm-up in that mode: arenas of the fixed size, two steps
-        step.run(n_views)                                       # in flight — the allocator's pool reaches its final size)
+    holder["cap"] = int(holder["maxR"] * 1.25) + 65536          # one arena size for all timed views from here on
+    for _ in range(3):                                          # (warm-up at that size: the allocator's pool reaches its
+        step.run(n_views)                                       # final state before anything is timed)
     barrier()
     check_capacity("warm-up")
 
@@ -489,7 +492,7 @@ def run_ours(args, cfg, rank, world, device):
 
     step_r = vp.ViewShardedStep(P, M, device, world=world, rank=rank, n_streams=args.streams, begin_view=begin_raster,
                                 finish_view=finish_raster, n_chunks=args.chunks, assignment=assignment,
-                                max_steps_ahead=None if args.waiting_forward else 1)
+                                max_steps_ahead=1 if args.no_wait_forward else None)
     holder["step"] = step_r
     for _ in range(4):
         step_r.run(n_views)
@@ -725,8 +728,8 @@ def main():
     ap.add_argument("--views-per-rank", type=int, default=8)
     ap.add_argument("--streams", type=int, default=2, help="views in flight per rank (CUDA streams)")
     ap.add_argument("--chunks", type=int, default=4, help="Gaussian ranges of the deferred per-Gaussian backward / all-reduce")
-    ap.add_argument("--waiting-forward", action="store_true",
-                    help="every forward waits for its instance count (the wrapper's default protocol) instead of no_wait + fixed capacity")
+    ap.add_argument("--no-wait-forward", action="store_true",
+                    help="timed legs: forwards never read the instance count back (no_wait), host bounded to one step ahead")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed regions")
     ap.add_argument("--nccl-normal-priority", action="store_true", help="N > 1: NCCL on a normal-priority stream (default: high)")
     ap.add_argument("--contiguous-views", action="store_true",

@@ -117,3 +117,18 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError, match="no CPU fallback"):
         _native.load()
+
+
+def test_capacity_hint_is_quantized():
+    """The automatic instance-capacity hint is rounded up to a small set of sizes (8-16 per octave, >= 64 Ki apart): arenas whose
+    size keeps changing miss torch's caching allocator and cost a cudaMalloc in the middle of a step."""
+    import diff_gaussian_rasterization as dgr
+    q = dgr._quantize_capacity
+    assert q(0) == 0 and q(-5) == 0 and q(1) == 65536
+    seen = set()
+    for c in range(6_500_000, 13_000_000, 9_973):
+        v = q(c)
+        assert c <= v <= c + max(c // 8, 65536) and q(v) == v
+        seen.add(v)
+    assert len(seen) <= 12                       # one octave of counts -> a handful of arena sizes
+    assert q((1 << 30) + 5) == (1 << 30) - 1 and all(q(c) <= q(c + 1) for c in range(1 << 20, (1 << 20) + 70000, 997))
