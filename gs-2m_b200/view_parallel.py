@@ -17,7 +17,11 @@ module does the same sum across a *batch* of views and across ranks:
   reduction logic is testable on CPU with the gloo backend.  Two protocols: ``render_view`` (a view's whole forward+backward
   in one call; one all-reduce at the end of the step) and ``begin_view`` / ``finish_view`` (the *deferred* step: a view's
   forward and reverse blend run as soon as possible, the per-Gaussian half of every view's backward runs afterwards, Gaussian
-  range by Gaussian range, and the all-reduce of a finished range overlaps the next range's kernels).
+  range by Gaussian range, and the all-reduce of a finished range overlaps the next range's kernels).  With ``finish_views`` a
+  range's per-Gaussian stage is one call for ALL of the rank's views (``backward_views_raw``: every output element written once
+  with the sum over the views); ``assignment`` replaces the contiguous split by a table (``balance_views``),
+  ``max_views_in_flight`` / ``max_steps_ahead`` bound the views that hold their arenas / the steps a non-waiting host may queue.
+* ``balance_views(costs, world)``        – equal view counts per rank, per-view costs (instance counts) dealt longest first.
 
 One process per GPU (torchrun); the path shards with no data-path collective other than this one exchange step.
 """
